@@ -1,0 +1,531 @@
+// bge-small-en encoder object behind the C ABI.
+//
+// Replaces HuggingFaceBgeEmbeddings -> SentenceTransformer.encode -> BertModel.forward ->
+// Pooling(cls) -> Normalize -> F.normalize (aidial_rag/embeddings/embeddings.py:52-66, :79-96)
+// on token ids.  The batch is PACKED (no padding): sequences sit back to back and
+// cu_seqlens marks their boundaries, so padded positions cost nothing and the attention
+// mask is implicit.
+//
+// Per forward:  embed+LN  ->  12 x { QKV GEMM | attention | out-proj GEMM + residual + LN |
+//               FFN-up GEMM + GELU | FFN-down GEMM + residual + LN }  ->  CLS + 2x L2 normalise.
+// All GEMMs are the tcgen05/TMA kernel of drag_gemm.cuh with fused epilogues.
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "drag_attention.cuh"
+#include "drag_common.cuh"
+#include "drag_gemm.cuh"
+
+namespace drag {
+namespace enc {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int HIDDEN = 384;
+constexpr int HEAD_DIM = 32;
+constexpr int QKV_BLOCK_N = 192;
+constexpr int FFN_BLOCK_N = 256;
+
+// ---------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// X[t] = LayerNorm(word[ids[t]] + pos[t - start(seq(t))] + type[0]); one warp per token,
+// each lane owns 12 of the 384 features (3 x float4, coalesced).
+__global__ void __launch_bounds__(256)
+embed_ln_kernel(const int* __restrict__ ids, const int* __restrict__ cu_seqlens, int n_seq, int total,
+                const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type0,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int vocab,
+                bf16* __restrict__ out, float* __restrict__ out_f32) {
+  const int tok = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (tok >= total) return;
+  int lo = 0, hi = n_seq;  // last s with cu[s] <= tok
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (cu_seqlens[mid] <= tok) lo = mid; else hi = mid;
+  }
+  const int p = tok - cu_seqlens[lo];
+  int id = ids[tok];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  float v[12];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int e = c * 128 + lane * 4;
+    float4 w = __ldg(reinterpret_cast<const float4*>(word + (size_t)id * HIDDEN + e));
+    float4 pp = __ldg(reinterpret_cast<const float4*>(pos + (size_t)p * HIDDEN + e));
+    float4 tt = __ldg(reinterpret_cast<const float4*>(type0 + e));
+    v[c * 4 + 0] = w.x + pp.x + tt.x; v[c * 4 + 1] = w.y + pp.y + tt.y;
+    v[c * 4 + 2] = w.z + pp.z + tt.z; v[c * 4 + 3] = w.w + pp.w + tt.w;
+    s += v[c * 4] + v[c * 4 + 1] + v[c * 4 + 2] + v[c * 4 + 3];
+  }
+  const float mean = warp_sum(s) * (1.f / HIDDEN);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) { float d = v[i] - mean; ss = fmaf(d, d, ss); }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.f / HIDDEN) + eps);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int e = c * 128 + lane * 4;
+    float4 g = __ldg(reinterpret_cast<const float4*>(gamma + e));
+    float4 b = __ldg(reinterpret_cast<const float4*>(beta + e));
+    float y0 = (v[c * 4 + 0] - mean) * rstd * g.x + b.x, y1 = (v[c * 4 + 1] - mean) * rstd * g.y + b.y;
+    float y2 = (v[c * 4 + 2] - mean) * rstd * g.z + b.z, y3 = (v[c * 4 + 3] - mean) * rstd * g.w + b.w;
+    uint2 packed = make_uint2(gemm::pack_bf16(y0, y1), gemm::pack_bf16(y2, y3));
+    *reinterpret_cast<uint2*>(out + (size_t)tok * HIDDEN + e) = packed;
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)tok * HIDDEN + e) = make_float4(y0, y1, y2, y3);
+  }
+}
+
+// out[s] = normalize(normalize(X[cu[s]]))  -- CLS pooling + the two F.normalize(p=2, eps=1e-12)
+__global__ void __launch_bounds__(256)
+pool_normalize_kernel(const bf16* __restrict__ x, const int* __restrict__ cu_seqlens, int n_seq, float* __restrict__ out) {
+  const int seq = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (seq >= n_seq) return;
+  const bf16* row = x + (size_t)cu_seqlens[seq] * HIDDEN;
+  float v[12];
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    uint2 raw = *reinterpret_cast<const uint2*>(row + c * 128 + lane * 4);
+    v[c * 4 + 0] = __uint_as_float(raw.x << 16); v[c * 4 + 1] = __uint_as_float(raw.x & 0xffff0000u);
+    v[c * 4 + 2] = __uint_as_float(raw.y << 16); v[c * 4 + 3] = __uint_as_float(raw.y & 0xffff0000u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ss = fmaf(v[c * 4 + i], v[c * 4 + i], ss);
+  }
+  float inv = 1.f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+  ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) { v[i] *= inv; ss = fmaf(v[i], v[i], ss); }
+  inv = 1.f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    *reinterpret_cast<float4*>(out + (size_t)seq * HIDDEN + c * 128 + lane * 4) =
+        make_float4(v[c * 4] * inv, v[c * 4 + 1] * inv, v[c * 4 + 2] * inv, v[c * 4 + 3] * inv);
+}
+
+__global__ void bf16_to_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(in[i]);
+}
+
+// ---------------------------------------------------------------------------------
+// host helpers
+// ---------------------------------------------------------------------------------
+static uint16_t f32_to_bf16_rne(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    else
+      cudaGetLastError();
+  });
+  return fn;
+}
+
+// bf16 row-major [rows, cols] -> TMA map with a (box_rows x 64) box and 128-byte swizzle
+static int make_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(DRAG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)gemm::BLOCK_K, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DRAG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return DRAG_OK;
+}
+
+struct Layer {
+  bf16 *w_qkv, *w_o, *w_up, *w_down;           // [1152,384] [384,384] [1536,384] [384,1536]
+  float *b_qkv, *b_o, *b_up, *b_down;
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  CUtensorMap tm_qkv, tm_o, tm_up, tm_down;
+};
+
+}  // namespace enc
+}  // namespace drag
+
+using namespace drag;
+using namespace drag::enc;
+
+struct drag_encoder {
+  drag_bert_shape shape;
+  int device = 0;
+  int sms = 0;
+  int64_t max_tokens = 0;  // padded to a multiple of 128
+  std::mutex lock;
+  std::vector<void*> allocs;
+  float *word = nullptr, *pos = nullptr, *type0 = nullptr, *emb_g = nullptr, *emb_b = nullptr;
+  std::vector<Layer> layers;
+  // activations (bf16)
+  bf16 *x = nullptr, *y = nullptr, *qkv = nullptr, *ctx = nullptr, *h = nullptr;
+  CUtensorMap tm_x, tm_y, tm_ctx, tm_h;
+  // host-buffer path
+  cudaStream_t stream = nullptr;
+  int32_t *d_ids = nullptr, *d_cu = nullptr;
+  float* d_out = nullptr;
+  int32_t *p_ids = nullptr, *p_cu = nullptr;
+  float* p_out = nullptr;
+  int64_t out_cap = 0;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(drag_encoder* e, T** out, size_t count) {
+  void* p = nullptr;
+  cudaError_t err = cudaMalloc(&p, count * sizeof(T) + 256);
+  if (err != cudaSuccess) {
+    cudaGetLastError();
+    return fail(DRAG_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(err));
+  }
+  e->allocs.push_back(p);
+  *out = (T*)p;
+  return DRAG_OK;
+}
+
+int upload_f32(drag_encoder* e, float** dst, const float* src, size_t n) {
+  int rc = dev_alloc(e, dst, n);
+  if (rc) return rc;
+  DRAG_CUDA_OK(cudaMemcpy(*dst, src, n * 4, cudaMemcpyHostToDevice));
+  return DRAG_OK;
+}
+
+// rows of several [r_i, cols] fp32 host matrices stacked into one bf16 device matrix
+int upload_bf16(drag_encoder* e, bf16** dst, std::initializer_list<const float*> srcs, size_t rows_each, size_t cols) {
+  const size_t n_each = rows_each * cols;
+  std::vector<uint16_t> tmp(n_each * srcs.size());
+  size_t off = 0;
+  for (const float* s : srcs) {
+    for (size_t i = 0; i < n_each; ++i) tmp[off + i] = f32_to_bf16_rne(s[i]);
+    off += n_each;
+  }
+  int rc = dev_alloc(e, dst, tmp.size());
+  if (rc) return rc;
+  DRAG_CUDA_OK(cudaMemcpy(*dst, tmp.data(), tmp.size() * 2, cudaMemcpyHostToDevice));
+  return DRAG_OK;
+}
+
+int upload_concat_f32(drag_encoder* e, float** dst, std::initializer_list<const float*> srcs, size_t n_each) {
+  std::vector<float> tmp;
+  for (const float* s : srcs) tmp.insert(tmp.end(), s, s + n_each);
+  return upload_f32(e, dst, tmp.data(), tmp.size());
+}
+
+template <int BLOCK_N, int EPI, int EPI_WARPS, int STAGES>
+int launch_gemm(const drag_encoder* e, const CUtensorMap& ta, const CUtensorMap& tw, const gemm::GemmParams& p, cudaStream_t st) {
+  auto kern = gemm::gemm_kernel<BLOCK_N, EPI, EPI_WARPS, STAGES>;
+  constexpr size_t smem = gemm::smem_bytes<BLOCK_N, STAGES>();
+  static std::once_flag once[16];
+  static cudaError_t attr_err[16];
+  const int dev_slot = e->device & 15;
+  std::call_once(once[dev_slot], [&] {
+    attr_err[dev_slot] = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  });
+  if (attr_err[dev_slot] != cudaSuccess)
+    return fail(DRAG_ERR_CUDA, "cudaFuncSetAttribute(gemm smem=%zu) failed: %s", smem, cudaGetErrorString(attr_err[dev_slot]));
+  const int m_tiles = (p.M + gemm::BLOCK_M - 1) / gemm::BLOCK_M;
+  const int tiles = m_tiles * (p.N / BLOCK_N);
+  const int grid = tiles < e->sms ? tiles : e->sms;
+  kern<<<grid, 64 + 32 * EPI_WARPS, smem, st>>>(ta, tw, p);
+  DRAG_CUDA_OK(cudaGetLastError());
+  return DRAG_OK;
+}
+
+int forward_impl(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu, const int32_t* h_cu, int n_seq,
+                 float* d_out, int stop_after_layer, float* d_hidden, cudaStream_t st) {
+  DRAG_REQUIRE(e && d_ids && d_cu && h_cu, "drag_encoder_forward: null pointer");
+  DRAG_REQUIRE(n_seq >= 0, "drag_encoder_forward: n_seq < 0");
+  if (n_seq == 0) return DRAG_OK;
+  DRAG_REQUIRE(h_cu[0] == 0, "drag_encoder_forward: cu_seqlens[0] must be 0");
+  int max_len = 0;
+  for (int i = 0; i < n_seq; ++i) {
+    const int len = h_cu[i + 1] - h_cu[i];
+    DRAG_REQUIRE(len >= 1 && len <= e->shape.max_pos, "drag_encoder_forward: sequence %d has length %d (allowed 1..%d)", i, len, e->shape.max_pos);
+    if (len > max_len) max_len = len;
+  }
+  const int total = h_cu[n_seq];
+  DRAG_REQUIRE((int64_t)total <= e->max_tokens, "drag_encoder_forward: %d tokens exceed max_tokens=%lld", total, (long long)e->max_tokens);
+  const drag_bert_shape& sh = e->shape;
+
+  const bool tap = d_hidden != nullptr;
+  {
+    const int warps_per_block = 8;
+    const int blocks = (total + warps_per_block - 1) / warps_per_block;
+    embed_ln_kernel<<<blocks, warps_per_block * 32, 0, st>>>(d_ids, d_cu, n_seq, total, e->word, e->pos, e->type0, e->emb_g,
+                                                            e->emb_b, sh.ln_eps, sh.vocab, e->x,
+                                                            (tap && stop_after_layer == 0) ? d_hidden : nullptr);
+    DRAG_CUDA_OK(cudaGetLastError());
+  }
+  const int n_layers = (tap && stop_after_layer < sh.layers) ? stop_after_layer : sh.layers;
+  const float scale_log2 = 1.4426950408889634f / sqrtf((float)HEAD_DIM);
+  const int s_pad = (max_len + 63) & ~63;
+  const size_t attn_smem = (size_t)2 * s_pad * attn::KV_STRIDE * sizeof(bf16);
+  for (int l = 0; l < n_layers; ++l) {
+    const Layer& L = e->layers[l];
+    gemm::GemmParams p{};
+    p.M = total;
+    p.ln_eps = sh.ln_eps;
+    // QKV projection
+    p.N = 3 * HIDDEN; p.K = HIDDEN; p.bias = L.b_qkv; p.out = e->qkv;
+    int rc = launch_gemm<QKV_BLOCK_N, gemm::EPI_BIAS, 4, 4>(e, e->tm_x, L.tm_qkv, p, st);
+    if (rc) return rc;
+    // attention
+    attn::attention_kernel<<<dim3(sh.heads, n_seq), attn::WARPS * 32, attn_smem, st>>>(e->qkv, e->ctx, d_cu, HIDDEN, scale_log2);
+    DRAG_CUDA_OK(cudaGetLastError());
+    // output projection + residual + LayerNorm
+    p.N = HIDDEN; p.K = HIDDEN; p.bias = L.b_o; p.gamma = L.ln1_g; p.beta = L.ln1_b; p.residual = e->x; p.out = e->y;
+    rc = launch_gemm<HIDDEN, gemm::EPI_BIAS_RES_LN, 8, 3>(e, e->tm_ctx, L.tm_o, p, st);
+    if (rc) return rc;
+    // FFN up + GELU
+    p.N = sh.inter; p.K = HIDDEN; p.bias = L.b_up; p.gamma = nullptr; p.beta = nullptr; p.residual = nullptr; p.out = e->h;
+    rc = launch_gemm<FFN_BLOCK_N, gemm::EPI_BIAS_GELU, 8, 4>(e, e->tm_y, L.tm_up, p, st);
+    if (rc) return rc;
+    // FFN down + residual + LayerNorm
+    p.N = HIDDEN; p.K = sh.inter; p.bias = L.b_down; p.gamma = L.ln2_g; p.beta = L.ln2_b; p.residual = e->y; p.out = e->x;
+    p.out_f32 = (tap && l + 1 == n_layers) ? d_hidden : nullptr;
+    rc = launch_gemm<HIDDEN, gemm::EPI_BIAS_RES_LN, 8, 3>(e, e->tm_h, L.tm_down, p, st);
+    if (rc) return rc;
+  }
+  if (d_out) {
+    const int blocks = (n_seq + 7) / 8;
+    pool_normalize_kernel<<<blocks, 256, 0, st>>>(e->x, d_cu, n_seq, d_out);
+    DRAG_CUDA_OK(cudaGetLastError());
+  }
+  return DRAG_OK;
+}
+
+}  // namespace
+
+extern "C" int drag_encoder_create(const drag_bert_shape* shape, const float* const* h_tensors, int n_tensors,
+                                   int device, int64_t max_tokens, drag_encoder** out) {
+  DRAG_REQUIRE(shape && h_tensors && out, "drag_encoder_create: null pointer");
+  *out = nullptr;
+  DRAG_REQUIRE(shape->hidden == HIDDEN, "drag_encoder_create: this build supports hidden=384 (got %d)", shape->hidden);
+  DRAG_REQUIRE(shape->heads * HEAD_DIM == shape->hidden, "drag_encoder_create: head_dim must be 32");
+  DRAG_REQUIRE(shape->inter % FFN_BLOCK_N == 0 && shape->inter % gemm::BLOCK_K == 0, "drag_encoder_create: intermediate size must be a multiple of 256");
+  DRAG_REQUIRE(shape->layers >= 1 && shape->vocab >= 1 && shape->max_pos >= 1 && shape->max_pos <= 512, "drag_encoder_create: bad shape");
+  DRAG_REQUIRE(n_tensors == 5 + 16 * shape->layers, "drag_encoder_create: expected %d tensors, got %d", 5 + 16 * shape->layers, n_tensors);
+  DRAG_REQUIRE(max_tokens >= 1 && max_tokens <= (1ll << 30), "drag_encoder_create: bad max_tokens");
+  for (int i = 0; i < n_tensors; ++i) DRAG_REQUIRE(h_tensors[i], "drag_encoder_create: tensor %d is null", i);
+  int n_dev = 0, cc = 0, sms = 0;
+  int rc = drag_device_info(device, &n_dev, &cc, &sms);
+  if (rc) return rc;
+  if (cc / 10 != 10) return fail(DRAG_ERR_DEVICE, "drag_encoder_create: device %d is sm_%d; this library is built for sm_100a only", device, cc);
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_encoder_create: cannot select device %d", device);
+
+  drag_encoder* e = new (std::nothrow) drag_encoder();
+  if (!e) return fail(DRAG_ERR_NOMEM, "drag_encoder_create: out of host memory");
+  e->shape = *shape;
+  e->device = device;
+  e->sms = sms;
+  e->max_tokens = (max_tokens + 127) / 128 * 128;
+  const size_t H = HIDDEN, F = shape->inter;
+  auto bail = [&](int code) { drag_encoder_destroy(e); return code; };
+
+  if ((rc = upload_f32(e, &e->word, h_tensors[0], (size_t)shape->vocab * H))) return bail(rc);
+  if ((rc = upload_f32(e, &e->pos, h_tensors[1], (size_t)shape->max_pos * H))) return bail(rc);
+  if ((rc = upload_f32(e, &e->type0, h_tensors[2], H))) return bail(rc);  // token_type 0 only
+  if ((rc = upload_f32(e, &e->emb_g, h_tensors[3], H))) return bail(rc);
+  if ((rc = upload_f32(e, &e->emb_b, h_tensors[4], H))) return bail(rc);
+  e->layers.resize(shape->layers);
+  for (int l = 0; l < shape->layers; ++l) {
+    const float* const* t = h_tensors + 5 + 16 * l;
+    Layer& L = e->layers[l];
+    if ((rc = upload_bf16(e, &L.w_qkv, {t[0], t[2], t[4]}, H, H))) return bail(rc);
+    if ((rc = upload_concat_f32(e, &L.b_qkv, {t[1], t[3], t[5]}, H))) return bail(rc);
+    if ((rc = upload_bf16(e, &L.w_o, {t[6]}, H, H))) return bail(rc);
+    if ((rc = upload_f32(e, &L.b_o, t[7], H))) return bail(rc);
+    if ((rc = upload_bf16(e, &L.w_up, {t[8]}, F, H))) return bail(rc);
+    if ((rc = upload_f32(e, &L.b_up, t[9], F))) return bail(rc);
+    if ((rc = upload_bf16(e, &L.w_down, {t[10]}, H, F))) return bail(rc);
+    if ((rc = upload_f32(e, &L.b_down, t[11], H))) return bail(rc);
+    if ((rc = upload_f32(e, &L.ln1_g, t[12], H))) return bail(rc);
+    if ((rc = upload_f32(e, &L.ln1_b, t[13], H))) return bail(rc);
+    if ((rc = upload_f32(e, &L.ln2_g, t[14], H))) return bail(rc);
+    if ((rc = upload_f32(e, &L.ln2_b, t[15], H))) return bail(rc);
+    if ((rc = make_tmap(&L.tm_qkv, L.w_qkv, 3 * H, H, gemm::Cfg<QKV_BLOCK_N>::UMMA_N))) return bail(rc);
+    if ((rc = make_tmap(&L.tm_o, L.w_o, H, H, gemm::Cfg<HIDDEN>::UMMA_N))) return bail(rc);
+    if ((rc = make_tmap(&L.tm_up, L.w_up, F, H, gemm::Cfg<FFN_BLOCK_N>::UMMA_N))) return bail(rc);
+    if ((rc = make_tmap(&L.tm_down, L.w_down, H, F, gemm::Cfg<HIDDEN>::UMMA_N))) return bail(rc);
+  }
+  const size_t T = (size_t)e->max_tokens;
+  if ((rc = dev_alloc(e, &e->x, T * H))) return bail(rc);
+  if ((rc = dev_alloc(e, &e->y, T * H))) return bail(rc);
+  if ((rc = dev_alloc(e, &e->ctx, T * H))) return bail(rc);
+  if ((rc = dev_alloc(e, &e->qkv, T * 3 * H))) return bail(rc);
+  if ((rc = dev_alloc(e, &e->h, T * F))) return bail(rc);
+  // activations are zeroed once so that the tail rows of the last 128-row tile hold finite values
+  cudaMemset(e->x, 0, T * H * 2); cudaMemset(e->y, 0, T * H * 2); cudaMemset(e->ctx, 0, T * H * 2);
+  cudaMemset(e->qkv, 0, T * 3 * H * 2); cudaMemset(e->h, 0, T * F * 2);
+  if ((rc = make_tmap(&e->tm_x, e->x, T, H, gemm::BLOCK_M))) return bail(rc);
+  if ((rc = make_tmap(&e->tm_y, e->y, T, H, gemm::BLOCK_M))) return bail(rc);
+  if ((rc = make_tmap(&e->tm_ctx, e->ctx, T, H, gemm::BLOCK_M))) return bail(rc);
+  if ((rc = make_tmap(&e->tm_h, e->h, T, F, gemm::BLOCK_M))) return bail(rc);
+
+  // host-buffer path: pinned staging + device mirrors
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(DRAG_ERR_CUDA, "cudaStreamCreate failed"));
+  if ((rc = dev_alloc(e, &e->d_ids, T))) return bail(rc);
+  if ((rc = dev_alloc(e, &e->d_cu, T + 1))) return bail(rc);
+  if (cudaMallocHost((void**)&e->p_ids, T * 4) != cudaSuccess || cudaMallocHost((void**)&e->p_cu, (T + 1) * 4) != cudaSuccess)
+    return bail(fail(DRAG_ERR_NOMEM, "cudaMallocHost failed"));
+  // attention kernel may need > 48 KB of dynamic shared memory (512-token sequences: 80 KB)
+  if (cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 512 * attn::KV_STRIDE * 2) != cudaSuccess)
+    return bail(fail(DRAG_ERR_CUDA, "cudaFuncSetAttribute(attention) failed: %s", cudaGetErrorString(cudaGetLastError())));
+  if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(DRAG_ERR_CUDA, "weight upload failed: %s", cudaGetErrorString(cudaGetLastError())));
+  *out = e;
+  return DRAG_OK;
+}
+
+extern "C" int drag_encoder_destroy(drag_encoder* e) {
+  if (!e) return DRAG_OK;
+  DeviceGuard guard(e->device);
+  if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
+  for (void* p : e->allocs) cudaFree(p);
+  if (e->p_ids) cudaFreeHost(e->p_ids);
+  if (e->p_cu) cudaFreeHost(e->p_cu);
+  if (e->p_out) cudaFreeHost(e->p_out);
+  if (e->d_out) cudaFree(e->d_out);
+  cudaGetLastError();
+  delete e;
+  return DRAG_OK;
+}
+
+extern "C" int drag_encoder_forward(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu_seqlens,
+                                    const int32_t* h_cu_seqlens, int n_seq, float* d_out, void* stream) {
+  DRAG_REQUIRE(e, "drag_encoder_forward: null encoder");
+  DRAG_REQUIRE(d_out || n_seq == 0, "drag_encoder_forward: null output");
+  std::lock_guard<std::mutex> hold(e->lock);
+  DeviceGuard guard(e->device);
+  if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_encoder_forward: cannot select device %d", e->device);
+  return forward_impl(e, d_ids, d_cu_seqlens, h_cu_seqlens, n_seq, d_out, -1, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int drag_encoder_forward_debug(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu_seqlens,
+                                          const int32_t* h_cu_seqlens, int n_seq, int stop_after_layer, float* d_hidden,
+                                          void* stream) {
+  DRAG_REQUIRE(e && d_hidden, "drag_encoder_forward_debug: null pointer");
+  DRAG_REQUIRE(stop_after_layer >= 0 && stop_after_layer <= e->shape.layers, "drag_encoder_forward_debug: bad layer %d", stop_after_layer);
+  std::lock_guard<std::mutex> hold(e->lock);
+  DeviceGuard guard(e->device);
+  if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_encoder_forward_debug: cannot select device %d", e->device);
+  return forward_impl(e, d_ids, d_cu_seqlens, h_cu_seqlens, n_seq, nullptr, stop_after_layer, d_hidden, (cudaStream_t)stream);
+}
+
+extern "C" int drag_encoder_embed_host(drag_encoder* e, const int32_t* h_ids, const int32_t* h_cu_seqlens, int n_seq,
+                                       float* h_out) {
+  DRAG_REQUIRE(e, "drag_encoder_embed_host: null encoder");
+  if (n_seq == 0) return DRAG_OK;
+  DRAG_REQUIRE(h_ids && h_cu_seqlens && h_out && n_seq > 0, "drag_encoder_embed_host: null pointer");
+  std::lock_guard<std::mutex> hold(e->lock);
+  DeviceGuard guard(e->device);
+  if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_encoder_embed_host: cannot select device %d", e->device);
+  const int64_t total = h_cu_seqlens[n_seq];
+  DRAG_REQUIRE(total >= n_seq && total <= e->max_tokens, "drag_encoder_embed_host: %lld tokens exceed max_tokens=%lld", (long long)total, (long long)e->max_tokens);
+  // output staging grows on demand (power-of-two capacity)
+  if (n_seq > e->out_cap) {
+    int64_t want = 1024;
+    while (want < n_seq) want <<= 1;
+    if (e->d_out) cudaFree(e->d_out);
+    if (e->p_out) cudaFreeHost(e->p_out);
+    e->d_out = nullptr; e->p_out = nullptr; e->out_cap = 0;
+    if (cudaMalloc((void**)&e->d_out, (size_t)want * HIDDEN * 4) != cudaSuccess ||
+        cudaMallocHost((void**)&e->p_out, (size_t)want * HIDDEN * 4) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(DRAG_ERR_NOMEM, "drag_encoder_embed_host: cannot allocate output staging for %lld sequences", (long long)want);
+    }
+    e->out_cap = want;
+  }
+  memcpy(e->p_ids, h_ids, (size_t)total * 4);
+  memcpy(e->p_cu, h_cu_seqlens, (size_t)(n_seq + 1) * 4);
+  DRAG_CUDA_OK(cudaMemcpyAsync(e->d_ids, e->p_ids, (size_t)total * 4, cudaMemcpyHostToDevice, e->stream));
+  DRAG_CUDA_OK(cudaMemcpyAsync(e->d_cu, e->p_cu, (size_t)(n_seq + 1) * 4, cudaMemcpyHostToDevice, e->stream));
+  int rc = forward_impl(e, e->d_ids, e->d_cu, e->p_cu, n_seq, e->d_out, -1, nullptr, e->stream);
+  if (rc) return rc;
+  DRAG_CUDA_OK(cudaMemcpyAsync(e->p_out, e->d_out, (size_t)n_seq * HIDDEN * 4, cudaMemcpyDeviceToHost, e->stream));
+  DRAG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  memcpy(h_out, e->p_out, (size_t)n_seq * HIDDEN * 4);
+  return DRAG_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// kernel-level entry points used by the parity tests to check each fused kernel in isolation
+// ---------------------------------------------------------------------------------
+extern "C" int drag_debug_gemm(int device, int variant, const void* d_a, const void* d_w, const float* d_bias,
+                               const float* d_gamma, const float* d_beta, const void* d_residual, void* d_out,
+                               int M, int N, int K, float ln_eps, void* stream) {
+  DRAG_REQUIRE(d_a && d_w && d_bias && d_out && M >= 1, "drag_debug_gemm: null pointer / empty problem");
+  DRAG_REQUIRE(K % gemm::BLOCK_K == 0 && K >= gemm::BLOCK_K, "drag_debug_gemm: K must be a multiple of 64");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_debug_gemm: cannot select device %d", device);
+  drag_encoder fake;
+  fake.device = device;
+  fake.sms = sm_count(device);
+  gemm::GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.bias = d_bias; p.gamma = d_gamma; p.beta = d_beta; p.ln_eps = ln_eps;
+  p.residual = (const bf16*)d_residual; p.out = (bf16*)d_out;
+  CUtensorMap ta, tw;
+  int rc = make_tmap(&ta, d_a, (uint64_t)M, (uint64_t)K, gemm::BLOCK_M);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (variant) {
+    case 0:
+      DRAG_REQUIRE(N % QKV_BLOCK_N == 0, "drag_debug_gemm: N must be a multiple of %d", QKV_BLOCK_N);
+      if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, gemm::Cfg<QKV_BLOCK_N>::UMMA_N))) return rc;
+      return launch_gemm<QKV_BLOCK_N, gemm::EPI_BIAS, 4, 4>(&fake, ta, tw, p, st);
+    case 1:
+      DRAG_REQUIRE(N % FFN_BLOCK_N == 0, "drag_debug_gemm: N must be a multiple of %d", FFN_BLOCK_N);
+      if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, gemm::Cfg<FFN_BLOCK_N>::UMMA_N))) return rc;
+      return launch_gemm<FFN_BLOCK_N, gemm::EPI_BIAS_GELU, 8, 4>(&fake, ta, tw, p, st);
+    case 2:
+      DRAG_REQUIRE(N == HIDDEN && d_gamma && d_beta && d_residual, "drag_debug_gemm: LN variant needs N=384, gamma, beta, residual");
+      if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, gemm::Cfg<HIDDEN>::UMMA_N))) return rc;
+      return launch_gemm<HIDDEN, gemm::EPI_BIAS_RES_LN, 8, 3>(&fake, ta, tw, p, st);
+    default:
+      return fail(DRAG_ERR_INVALID, "drag_debug_gemm: unknown variant %d", variant);
+  }
+}
+
+extern "C" int drag_debug_attention(int device, const void* d_qkv, void* d_ctx, const int32_t* d_cu_seqlens, int n_seq,
+                                    int max_len, int heads, void* stream) {
+  DRAG_REQUIRE(d_qkv && d_ctx && d_cu_seqlens && n_seq >= 1 && heads >= 1, "drag_debug_attention: bad arguments");
+  DRAG_REQUIRE(max_len >= 1 && max_len <= 512, "drag_debug_attention: max_len must be in 1..512");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_debug_attention: cannot select device %d", device);
+  DRAG_CUDA_OK(cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 512 * attn::KV_STRIDE * 2));
+  const int s_pad = (max_len + 63) & ~63;
+  const size_t smem = (size_t)2 * s_pad * attn::KV_STRIDE * sizeof(bf16);
+  const float scale_log2 = 1.4426950408889634f / sqrtf((float)HEAD_DIM);
+  attn::attention_kernel<<<dim3(heads, n_seq), attn::WARPS * 32, smem, (cudaStream_t)stream>>>(
+      (const bf16*)d_qkv, (bf16*)d_ctx, d_cu_seqlens, heads * HEAD_DIM, scale_log2);
+  DRAG_CUDA_OK(cudaGetLastError());
+  return DRAG_OK;
+}

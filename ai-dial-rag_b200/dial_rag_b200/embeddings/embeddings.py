@@ -1,0 +1,155 @@
+"""bge-small-en embeddings on the B200 -- drop-in for aidial_rag/embeddings/embeddings.py.
+
+Same module surface: ``bge_embedding`` (an ``AsyncEmbeddings``), ``bge_embedding_impl()``,
+``build_embeddings(texts, stageio)``, ``EMBEDDING_LENGTH``, ``EMBEDDINGS_BATCH_SIZE``,
+``BGE_EMBEDDINGS_MODEL_NAME_OR_PATH``, ``BGE_EMBEDDINGS_DEVICE``.
+
+What changes is the execution: ``bge_embedding_impl()`` returns a ``B200BgeEmbeddings``
+whose ``embed_documents`` / ``embed_query`` keep the text preparation of langchain's
+``HuggingFaceBgeEmbeddings`` (newlines -> spaces; query instruction prefix) and
+sentence-transformers' truncation, tokenise on the host and run the hand-written CUDA
+encoder (packed batches, no padding) through the C ABI.
+
+Differences from the reference, all deliberate:
+  * the model is created on first use, not at import (embeddings.py:69 runs a forward at
+    import to learn the width); ``EMBEDDING_LENGTH`` is the constant 384;
+  * ``AsyncEmbeddings.embed_documents/embed_query`` work synchronously instead of raising
+    ``NotImplementedError`` (embeddings.py:73-77) -- ``SemanticRetriever._get_relevant_documents``
+    calls the sync form (semantic_retriever.py:49);
+  * ``aembed_documents_numpy`` returns views of one float32 matrix, skipping the
+    ``List[float]`` round trip the reference marks as TODO (embeddings.py:87).
+"""
+
+from __future__ import annotations
+
+import logging
+import os
+import threading
+from typing import Iterable, List, Mapping, Optional, Sequence
+
+import numpy as np
+
+from dial_rag_b200.batched import batched_map_with_progress
+from dial_rag_b200.embeddings.detect_device import DeviceType, detect_device
+from dial_rag_b200.embeddings.encoder import BGE_SMALL, B200Encoder, EncoderShape, load_model_dir
+from dial_rag_b200.embeddings.tokenizer import WordPieceTokenizer
+from dial_rag_b200.resources.cpu_pools import run_in_indexing_embeddings_pool, run_in_query_embeddings_pool
+
+try:  # use langchain's base class when the package lives inside a Dial RAG deployment
+    from langchain.schema.embeddings import Embeddings  # type: ignore
+except Exception:  # noqa: BLE001
+    try:
+        from langchain_core.embeddings import Embeddings  # type: ignore
+    except Exception:  # noqa: BLE001
+
+        class Embeddings:  # type: ignore[no-redef]
+            """Minimal stand-in for langchain's ``Embeddings`` interface."""
+
+            def embed_documents(self, texts: List[str]) -> List[List[float]]:
+                raise NotImplementedError
+
+            def embed_query(self, text: str) -> List[float]:
+                raise NotImplementedError
+
+
+logger = logging.getLogger(__name__)
+
+# The reference uses 128 ("works faster on CPU with openvino", embeddings.py:24-26).  One outer
+# batch is one executor submission and one packed GPU forward; 1024 chunks keep the B200 busy
+# (>= 1k 128-row tiles per GEMM) while still interleaving requests batch by batch.
+EMBEDDINGS_BATCH_SIZE = int(os.environ.get("DIAL_RAG_B200_EMBEDDINGS_BATCH_SIZE", "1024"))
+
+BGE_EMBEDDINGS_MODEL_NAME_OR_PATH = os.environ.get("BGE_EMBEDDINGS_MODEL_PATH", "epam/bge-small-en")
+BGE_EMBEDDINGS_DEVICE = os.environ.get("BGE_EMBEDDINGS_DEVICE", DeviceType.AUTO)
+
+# langchain_community.embeddings.huggingface.DEFAULT_QUERY_BGE_INSTRUCTION_EN
+DEFAULT_QUERY_BGE_INSTRUCTION_EN = "Represent this question for searching relevant passages: "
+
+EMBEDDING_LENGTH = BGE_SMALL.hidden
+
+
+class B200BgeEmbeddings(Embeddings):
+    """``HuggingFaceBgeEmbeddings`` look-alike backed by the CUDA encoder."""
+
+    query_instruction: str = DEFAULT_QUERY_BGE_INSTRUCTION_EN
+    embed_instruction: str = ""
+
+    def __init__(self, weights: Mapping[str, object], tokenizer: WordPieceTokenizer,
+                 shape: EncoderShape = BGE_SMALL, device: int = 0, max_tokens: int = 262144):
+        self.tokenizer = tokenizer
+        self.client = B200Encoder(weights, shape=shape, device=device, max_tokens=max_tokens)
+
+    @classmethod
+    def from_model_dir(cls, path: str, device: int = 0, **kw) -> "B200BgeEmbeddings":
+        return cls(load_model_dir(path), WordPieceTokenizer.from_model_dir(path), device=device, **kw)
+
+    def embed_documents_numpy(self, texts: Sequence[str]) -> np.ndarray:
+        prepared = [self.embed_instruction + t.replace("\n", " ") for t in texts]
+        return self.client.embed_token_lists(self.tokenizer.encode_batch(prepared))
+
+    def embed_documents(self, texts: List[str]) -> List[List[float]]:
+        return self.embed_documents_numpy(texts).tolist()
+
+    def embed_query(self, text: str) -> List[float]:
+        prepared = self.query_instruction + text.replace("\n", " ")
+        return self.client.embed_token_lists(self.tokenizer.encode_batch([prepared]))[0].tolist()
+
+
+_impl: Optional[B200BgeEmbeddings] = None
+_impl_lock = threading.Lock()
+
+
+def configure(impl: Optional[B200BgeEmbeddings]) -> None:
+    """Install (or clear) the process-wide encoder, e.g. with seeded weights in tests/bench."""
+    global _impl
+    with _impl_lock:
+        _impl = impl
+
+
+def bge_embedding_impl() -> B200BgeEmbeddings:
+    """Process-wide encoder, created on first use (reference: ``@cache``, embeddings.py:52-66)."""
+    global _impl
+    if _impl is None:
+        with _impl_lock:
+            if _impl is None:
+                device = detect_device(BGE_EMBEDDINGS_DEVICE)
+                if device == DeviceType.CPU:
+                    raise RuntimeError(
+                        "dial_rag_b200 has no CPU execution path: BGE_EMBEDDINGS_DEVICE must be auto/cuda/b200 "
+                        "on a machine with an sm_100 GPU")
+                if not os.path.isdir(BGE_EMBEDDINGS_MODEL_NAME_OR_PATH):
+                    raise FileNotFoundError(
+                        f"BGE_EMBEDDINGS_MODEL_PATH={BGE_EMBEDDINGS_MODEL_NAME_OR_PATH!r} is not a directory with "
+                        "model.safetensors + tokenizer.json (no hub download: the deployment image bakes the model in, "
+                        "reference Dockerfile:61)")
+                logger.info("BGE embeddings device: b200 (cuda:%s)", os.environ.get("DIAL_RAG_B200_DEVICE", "0"))
+                _impl = B200BgeEmbeddings.from_model_dir(
+                    BGE_EMBEDDINGS_MODEL_NAME_OR_PATH, device=int(os.environ.get("DIAL_RAG_B200_DEVICE", "0")))
+    return _impl
+
+
+class AsyncEmbeddings(Embeddings):
+    def embed_documents(self, texts: List[str]) -> List[List[float]]:
+        return bge_embedding_impl().embed_documents(texts)
+
+    def embed_query(self, text: str) -> List[float]:
+        return bge_embedding_impl().embed_query(text)
+
+    async def aembed_documents(self, texts: List[str]) -> List[List[float]]:
+        return await run_in_indexing_embeddings_pool(bge_embedding_impl().embed_documents, texts)
+
+    async def aembed_documents_numpy(self, texts: List[str]) -> List[np.ndarray]:
+        matrix = await run_in_indexing_embeddings_pool(bge_embedding_impl().embed_documents_numpy, texts)
+        return list(matrix)  # float32 row views, shape (384,)
+
+    async def aembed_query(self, text: str) -> List[float]:
+        return await run_in_query_embeddings_pool(bge_embedding_impl().embed_query, text)
+
+
+bge_embedding = AsyncEmbeddings()
+
+
+async def build_embeddings(texts: Iterable[str], stageio):
+    """Embed ``texts`` in order, batch by batch, with progress lines (embeddings.py:102-108)."""
+    return await batched_map_with_progress(
+        texts, bge_embedding.aembed_documents_numpy, EMBEDDINGS_BATCH_SIZE, file=stageio)

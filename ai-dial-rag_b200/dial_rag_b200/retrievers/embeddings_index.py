@@ -1,0 +1,226 @@
+"""Embeddings index with GPU search -- drop-in for aidial_rag/retrievers/embeddings_index.py.
+
+Same public surface (``DocIndex``, ``EmbeddingsIndex(retrieval_type, indexes, metric,
+limit).find/find_in_doc``, ``create_index_by_chunk/page``, ``pack_simple/multi_embeddings``,
+``to_ndarray``) and the same results; the execution differs:
+
+* the per-document matrices are concatenated once, in document order, into ONE
+  row-major device matrix with a document-offset table.  The reference's
+  "per-document stable top-k, then stable top-k of the concatenated winners"
+  (embeddings_index.py:62-89) equals one global stable top-k over that concatenation
+  (ties -> earlier document, then lower row == lowest global row id), so a single
+  fused scan answers ``find``;
+* scoring + selection is ``drag_topk`` (float64 accumulation like numpy's path,
+  NaN last like ``np.argsort``), row -> (doc_id, chunk_id) is ``drag_rows_to_chunks``.
+"""
+
+from __future__ import annotations
+
+import threading
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import numpy.typing as npt
+
+from dial_rag_b200.device_index import DeviceMatrix
+from dial_rag_b200.records import (
+    Chunk,
+    Document,
+    ItemEmbeddings,
+    MultiEmbeddings,
+    RetrievalType,
+    to_metadata_doc,
+)
+from dial_rag_b200.retrievers.embeddings_metrics import Metric
+
+__all__ = [
+    "DocIndex", "EmbeddingsIndex", "Metric", "create_index_by_chunk", "create_index_by_page",
+    "pack_multi_embeddings", "pack_simple_embeddings", "to_ndarray",
+]
+
+
+class DocIndex:
+    """Row -> chunk map and embedding rows of one document (embeddings_index.py:14-30)."""
+
+    chunk_ids: npt.NDArray[np.int64]
+    embeddings: np.ndarray
+
+    def __init__(self, chunk_ids: npt.NDArray[np.int64] | None = None, embeddings: np.ndarray | None = None):
+        self.chunk_ids = np.array([], dtype=np.int64) if chunk_ids is None else chunk_ids
+        self.embeddings = np.array([], dtype=np.float32) if embeddings is None else embeddings
+        self._device: Optional[DeviceMatrix] = None
+
+    def __len__(self) -> int:
+        return len(self.embeddings)
+
+
+def _stack_documents(doc_indexes: Sequence[DocIndex]):
+    """Concatenate non-empty documents in order; offsets repeat for empty ones."""
+    mats, ids, offsets = [], [], [0]
+    dim = None
+    for doc in doc_indexes:
+        n = len(doc.embeddings)
+        if n:
+            emb = np.asarray(doc.embeddings)
+            if emb.ndim != 2:
+                raise ValueError(f"document embeddings must be 2-d, got shape {emb.shape}")
+            if dim is None:
+                dim = emb.shape[1]
+            elif emb.shape[1] != dim:
+                raise ValueError(f"embedding dimension mismatch between documents: {dim} vs {emb.shape[1]}")
+            if len(doc.chunk_ids) != n:
+                raise ValueError("chunk_ids and embeddings must have the same length")
+            mats.append(np.ascontiguousarray(emb, dtype=np.float32))
+            ids.append(np.asarray(doc.chunk_ids, dtype=np.int64))
+        offsets.append(offsets[-1] + n)
+    if not mats:
+        return None, None, offsets
+    return np.concatenate(mats), np.concatenate(ids), offsets
+
+
+class EmbeddingsIndex:
+    retrieval_type: RetrievalType
+    doc_indexes: List[DocIndex]
+    metric: str
+    limit: int
+
+    def __init__(
+        self,
+        retrieval_type: RetrievalType,
+        indexes: List[DocIndex],
+        metric: Metric = Metric.SQEUCLIDEAN_DIST,
+        limit: int = 1,
+        device: Optional[int] = None,
+        storage: str = "f32",
+    ):
+        self.retrieval_type = retrieval_type
+        self.metric = metric
+        self.limit = limit
+        self.doc_indexes = indexes
+        self._device_id = device
+        self._storage = storage
+        self._resident: Optional[DeviceMatrix] = None
+        self._resident_empty = False
+        self._lock = threading.Lock()
+
+    # The matrix is uploaded on first use and then stays in HBM for the life of the
+    # index object (the reference rebuilds host arrays per request, retrieval_chain.py:264-271).
+    def _matrix(self) -> Optional[DeviceMatrix]:
+        if self._resident is None and not self._resident_empty:
+            with self._lock:
+                if self._resident is None and not self._resident_empty:
+                    flat, ids, offsets = _stack_documents(self.doc_indexes)
+                    if flat is None:
+                        self._resident_empty = True
+                    else:
+                        self._resident = DeviceMatrix(
+                            flat, device=self._device_id, storage=self._storage,
+                            chunk_ids=ids, doc_offsets=offsets,
+                        )
+        return self._resident
+
+    def find_in_doc(
+        self, query: np.ndarray, doc_index: DocIndex
+    ) -> Tuple[npt.NDArray[np.int64], npt.NDArray[np.float64]]:
+        """Top ``limit`` rows of one document: ``(chunk_ids, distances)`` (embeddings_index.py:51-60)."""
+        if len(doc_index.embeddings) == 0:
+            return np.array([], dtype=np.int64), np.array([], dtype=np.float64)
+        if doc_index._device is None:
+            doc_index._device = DeviceMatrix(
+                np.asarray(doc_index.embeddings), device=self._device_id, storage=self._storage,
+                chunk_ids=np.asarray(doc_index.chunk_ids, dtype=np.int64),
+            )
+        _, chunks, dist = doc_index._device.topk_chunks(np.asarray(query), self.limit, Metric(self.metric))
+        return chunks[0], dist[0]
+
+    def find(self, query: np.ndarray) -> List[Document]:
+        """embeddings_index.py:62-89 for one query vector."""
+        return self.find_batch(np.asarray(query)[None, :])[0]
+
+    def find_batch(self, queries: np.ndarray) -> List[List[Document]]:
+        """``find`` for many query vectors sharing one pass over the matrix."""
+        queries = np.asarray(queries)
+        matrix = self._matrix()
+        if matrix is None:
+            return [[] for _ in range(len(queries))]
+        docs, chunks, _ = matrix.topk_chunks(queries, self.limit, Metric(self.metric))
+        return [
+            [
+                to_metadata_doc(int(d), int(c), retrieval_type=self.retrieval_type)
+                for d, c in zip(docs[i], chunks[i], strict=True)
+            ]
+            for i in range(len(queries))
+        ]
+
+
+def _get_page_index(chunk: Chunk) -> int:
+    # page numbers are 1-based in chunk metadata (embeddings_index.py:92-94)
+    return chunk.metadata["page_number"] - 1
+
+
+def to_ndarray(arr: np.ndarray):
+    """Wrap as docarray ``NdArray`` when docarray is present (embeddings_index.py:97-98)."""
+    try:
+        from docarray.typing import NdArray  # type: ignore
+
+        return NdArray(shape=arr.shape, buffer=arr, dtype=arr.dtype)
+    except Exception:  # noqa: BLE001
+        return arr
+
+
+def _rows_of(item) -> np.ndarray:
+    return np.asarray(item.embeddings)
+
+
+def create_index_by_page(chunks: Sequence[Chunk], pages_embeddings: MultiEmbeddings | None) -> DocIndex:
+    """Every chunk gets all rows of its page (embeddings_index.py:101-118)."""
+    if pages_embeddings is None:
+        return DocIndex()
+    owners, blocks = [], []
+    for i, chunk in enumerate(chunks):
+        rows = _rows_of(pages_embeddings[_get_page_index(chunk)])
+        owners.append(np.full(len(rows), i, dtype=np.int64))
+        if len(rows):
+            blocks.append(rows.reshape(len(rows), -1))
+    if not blocks:
+        return DocIndex(np.array([], dtype=np.int64), np.array([], dtype=np.float32))
+    return DocIndex(chunk_ids=np.concatenate(owners), embeddings=np.concatenate(blocks).astype(np.float32, copy=False))
+
+
+def create_index_by_chunk(chunks_embeddings: MultiEmbeddings | None) -> DocIndex:
+    """Item i owns ``len(item.embeddings)`` consecutive rows (embeddings_index.py:121-136)."""
+    if chunks_embeddings is None:
+        return DocIndex()
+    owners, blocks = [], []
+    for i, item in enumerate(chunks_embeddings):
+        rows = _rows_of(item)
+        owners.append(np.full(len(rows), i, dtype=np.int64))
+        if len(rows):
+            blocks.append(rows.reshape(len(rows), -1))
+    if not blocks:
+        return DocIndex(np.array([], dtype=np.int64), np.array([], dtype=np.float32))
+    return DocIndex(chunk_ids=np.concatenate(owners), embeddings=np.concatenate(blocks))
+
+
+def pack_multi_embeddings(indexes: List[int], embeddings: Iterable[np.ndarray], number_of_pages: int) -> MultiEmbeddings:
+    """Group embeddings by page index (embeddings_index.py:139-153)."""
+    per_page: List[List[np.ndarray]] = [[] for _ in range(number_of_pages)]
+    for page, emb in zip(indexes, embeddings, strict=True):
+        per_page[page].append(emb)
+    return MultiEmbeddings(
+        [ItemEmbeddings(embeddings=to_ndarray(np.array(rows, dtype=np.float32))) for rows in per_page]
+    )
+
+
+def pack_simple_embeddings(embeddings: Iterable[np.ndarray]) -> MultiEmbeddings:
+    """One ``[1, dim]`` float32 array per chunk (embeddings_index.py:156-164)."""
+    return MultiEmbeddings(
+        [ItemEmbeddings(embeddings=to_ndarray(np.asarray(e, dtype=np.float32)[None, :])) for e in embeddings]
+    )
+
+
+def pack_embedding_matrix(matrix: np.ndarray) -> MultiEmbeddings:
+    """Zero-copy variant of ``pack_simple_embeddings`` for an ``[n, dim]`` float32 matrix:
+    every item is a ``[1, dim]`` view into ``matrix``."""
+    matrix = np.ascontiguousarray(matrix, dtype=np.float32)
+    return MultiEmbeddings([ItemEmbeddings(embeddings=to_ndarray(matrix[i : i + 1])) for i in range(len(matrix))])

@@ -1,0 +1,202 @@
+/*
+ * drag_b200.h -- C ABI of the B200-native semantic-retriever hot path for Dial RAG.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no
+ * torch/pybind types.  The reference (epam/ai-dial-rag, pure Python) has no FFI
+ * for this path today; each entry point below names the reference code it
+ * replaces (paths relative to the reference repo) and INTEGRATION.md shows the
+ * ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a DRAG_ERR_* code otherwise and never
+ *     throws; drag_last_error() returns a thread-local message for the last
+ *     failure on the calling thread;
+ *   - "d_" pointers are DEVICE pointers owned by the caller (e.g. a torch tensor's
+ *     data_ptr()) and must stay valid until the work queued on `stream` is done;
+ *     "h_" pointers are HOST pointers;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - functions are re-entrant; an encoder object serialises its own callers with
+ *     an internal lock (the reference's 1-worker pools may still issue an indexing
+ *     and a query call at the same time, aidial_rag/resources/cpu_pools.py:50-59).
+ */
+#ifndef DRAG_B200_H_
+#define DRAG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRAG_ABI_VERSION 1
+
+enum drag_status {
+  DRAG_OK = 0,
+  DRAG_ERR_INVALID = 1,     /* bad argument */
+  DRAG_ERR_CUDA = 2,        /* CUDA runtime/driver error (message has details) */
+  DRAG_ERR_UNSUPPORTED = 3, /* shape outside what the kernels implement */
+  DRAG_ERR_NOMEM = 4,
+  DRAG_ERR_DEVICE = 5       /* no sm_100 device / wrong architecture */
+};
+
+/* aidial_rag/retrievers/embeddings_metrics.py:7-11 (enum Metric) */
+enum drag_metric {
+  DRAG_METRIC_COSINE_SIM = 0,
+  DRAG_METRIC_EUCLIDEAN_DIST = 1,
+  DRAG_METRIC_SQEUCLIDEAN_DIST = 2,
+  DRAG_METRIC_INNER_PRODUCT = 3
+};
+
+enum drag_dtype { DRAG_F32 = 0, DRAG_BF16 = 1 };
+
+const char* drag_last_error(void);
+int drag_abi_version(void);
+/* Number of CUDA devices and compute capability (major*10+minor) of `device`. */
+int drag_device_info(int device, int* n_devices, int* compute_capability, int* sm_count);
+
+/* ------------------------------------------------------------------------- *
+ *  Encoder: bge-small-en style BERT -> CLS -> L2 normalise                   *
+ *  replaces HuggingFaceBgeEmbeddings/SentenceTransformer.encode as used by   *
+ *  aidial_rag/embeddings/embeddings.py:52-66 (construction), :79-96 (calls). *
+ * ------------------------------------------------------------------------- */
+
+typedef struct drag_encoder drag_encoder;
+
+typedef struct drag_bert_shape {
+  int32_t vocab;      /* 30522 */
+  int32_t hidden;     /* 384   (must be 384 in this build) */
+  int32_t layers;     /* 12    */
+  int32_t heads;      /* 12    (head_dim must be 32) */
+  int32_t inter;      /* 1536  */
+  int32_t max_pos;    /* 512   */
+  int32_t type_vocab; /* 2     */
+  float ln_eps;       /* 1e-12 */
+} drag_bert_shape;
+
+/*
+ * h_tensors: n_tensors host fp32 arrays in HF BertModel state-dict order:
+ *   word_embeddings, position_embeddings, token_type_embeddings, emb LN weight, emb LN bias,
+ *   then per layer: q.w q.b k.w k.b v.w v.b attn_out.w attn_out.b inter.w inter.b out.w out.b
+ *                   attn_LN.w attn_LN.b out_LN.w out_LN.b          (5 + 16*layers tensors)
+ * Linear weights are [out, in] row-major exactly as stored by HF.  They are
+ * converted to bf16 and uploaded to `device`; nothing is borrowed after return.
+ * max_tokens bounds the packed token count of one forward call (workspace size).
+ * Replaces bge_embedding_impl() (embeddings.py:52-66).
+ */
+int drag_encoder_create(const drag_bert_shape* shape, const float* const* h_tensors,
+                        int n_tensors, int device, int64_t max_tokens, drag_encoder** out);
+int drag_encoder_destroy(drag_encoder* enc);
+
+/*
+ * One forward over a packed (padding-free) batch resident on the device.
+ *   d_ids        int32[total_tokens]  token ids, sequences back to back
+ *   d_cu_seqlens int32[n_seq + 1]     prefix sums of sequence lengths (cu[0] = 0)
+ *   h_cu_seqlens same values on the host (needed to plan the launch)
+ *   d_out        f32[n_seq, hidden]   L2-normalised CLS embeddings
+ * Every sequence length must be in [1, max_pos].  Asynchronous on `stream`.
+ * Replaces SentenceTransformer.encode -> BertModel.forward -> Pooling(cls) ->
+ * Normalize -> F.normalize (call sites embeddings.py:80-82, :94-96).
+ */
+int drag_encoder_forward(drag_encoder* enc, const int32_t* d_ids, const int32_t* d_cu_seqlens,
+                         const int32_t* h_cu_seqlens, int n_seq, float* d_out, void* stream);
+
+/*
+ * Host-buffer form of the same call (what HuggingFaceBgeEmbeddings.embed_documents
+ * hands back to embeddings.py:84-91): token ids in, float32 rows out, host memory on
+ * both sides; copies, forward and synchronisation happen inside.
+ */
+int drag_encoder_embed_host(drag_encoder* enc, const int32_t* h_ids, const int32_t* h_cu_seqlens,
+                            int n_seq, float* h_out);
+
+/* Device-side debug taps used by the parity tests (layer = 0 -> embedding LayerNorm
+ * output, l -> output of encoder layer l).  d_hidden: f32[total_tokens, hidden]. */
+int drag_encoder_forward_debug(drag_encoder* enc, const int32_t* d_ids, const int32_t* d_cu_seqlens,
+                               const int32_t* h_cu_seqlens, int n_seq, int stop_after_layer,
+                               float* d_hidden, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ *  Index: row norms + exact top-k                                            *
+ *  replaces ENUM_TO_METRIC[...] + np.argsort(kind="stable")[:limit] of       *
+ *  aidial_rag/retrievers/embeddings_index.py:51-89 and                       *
+ *  aidial_rag/retrievers/embeddings_metrics.py:14-50.                        *
+ * ------------------------------------------------------------------------- */
+
+/*
+ * d_out[i] = float32 sum of squares of row i, evaluated in numpy's pairwise order
+ * so that it equals `np.sum(docs**2, axis=1)` (embeddings_metrics.py:40) bit for bit.
+ * Needed once per index for the (sq)euclidean metrics.
+ */
+int drag_row_sqnorm(const void* d_matrix, int dtype, int64_t n_rows, int dim,
+                    float* d_out, void* stream);
+
+/*
+ * All distances of ONE query to every row: d_out[i] = ENUM_TO_METRIC[metric](query, docs)[i]
+ * (embeddings_metrics.py:53-58), float64.  d_scratch16: 16 bytes of device scratch.
+ */
+int drag_distances(int device, const void* d_matrix, int dtype, int64_t n_rows, int dim,
+                   const float* d_row_sqnorm, const double* d_query, int metric, double* d_out,
+                   void* d_scratch16, void* stream);
+
+/* Bytes of scratch drag_topk needs for (n_queries, k) on `device`. */
+int drag_topk_workspace_bytes(int device, int n_queries, int k, size_t* bytes);
+
+/*
+ * Exact top-k of every query against one row-major matrix shard.
+ *   d_matrix     [n_rows, dim] f32 or bf16, row-major, dense
+ *   d_row_sqnorm f32[n_rows] from drag_row_sqnorm (may be NULL for cosine / inner product)
+ *   d_queries    f64[n_queries, dim]  (the reference's query is float64,
+ *                aidial_rag/retrievers/semantic_retriever.py:49,53)
+ *   row_id_base  added to local row numbers (row-sharded index: shard offset)
+ *   d_out_dist   f64[n_queries, k]  "smaller is better" distance, ascending
+ *   d_out_row    i64[n_queries, k]  global row id; ties -> lowest row id
+ *                (== earlier document, then lower row: embeddings_index.py:58,81)
+ *   d_out_count  i32[n_queries]     min(k, n_rows) valid entries per query
+ * Scores are accumulated in float64 like the reference's numpy path; NaN
+ * distances (sqrt of a negative rounding residue, embeddings_metrics.py:50) sort
+ * last, as numpy's argsort does.  Asynchronous on `stream`.
+ */
+int drag_topk(int device, const void* d_matrix, int dtype, int64_t n_rows, int dim,
+              const float* d_row_sqnorm, const double* d_queries, int n_queries, int k,
+              int metric, int64_t row_id_base, double* d_out_dist, int64_t* d_out_row,
+              int32_t* d_out_count, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Merge per-shard results (after an all-gather) into the global top-k.
+ *   d_in_dist/d_in_row/d_in_count : [n_shards, n_queries, k] / [n_shards, n_queries]
+ * Same ordering rule as drag_topk.  Output arrays as in drag_topk.
+ */
+int drag_topk_merge(int device, const double* d_in_dist, const int64_t* d_in_row,
+                    const int32_t* d_in_count, int n_shards, int n_queries, int k,
+                    double* d_out_dist, int64_t* d_out_row, int32_t* d_out_count, void* stream);
+
+/*
+ * Map winning global rows to (document, chunk) pairs: doc = the i with
+ * d_doc_offsets[i] <= row < d_doc_offsets[i+1] (empty documents are skipped, as in
+ * embeddings_index.py:67-68), chunk = d_row_chunk_ids[row] (embeddings_index.py:60).
+ */
+int drag_rows_to_chunks(const int64_t* d_rows, int64_t n, const int64_t* d_doc_offsets,
+                        int n_docs, const int64_t* d_row_chunk_ids, int64_t* d_out_doc,
+                        int64_t* d_out_chunk, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ *  Kernel-level entry points (parity tests only): run ONE fused kernel.      *
+ * ------------------------------------------------------------------------- */
+
+/*
+ * OUT[M,N] = epilogue(A[M,K] . W[N,K]^T + bias), bf16 in/out, fp32 accumulate (tcgen05).
+ *   variant 0: +bias (QKV projection, N % 192 == 0)     1: +bias, erf-GELU (N % 256 == 0)
+ *   variant 2: +bias +residual, LayerNorm(gamma, beta, ln_eps) over N == 384
+ */
+int drag_debug_gemm(int device, int variant, const void* d_a, const void* d_w, const float* d_bias,
+                    const float* d_gamma, const float* d_beta, const void* d_residual, void* d_out,
+                    int M, int N, int K, float ln_eps, void* stream);
+
+/* ctx[T, heads*32] = softmax(Q K^T / sqrt(32)) V per packed sequence; d_qkv is bf16 [T, 3*heads*32]. */
+int drag_debug_attention(int device, const void* d_qkv, void* d_ctx, const int32_t* d_cu_seqlens,
+                         int n_seq, int max_len, int heads, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRAG_B200_H_ */

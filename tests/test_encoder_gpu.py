@@ -1,0 +1,182 @@
+"""GPU parity of the embedding half: each fused kernel in isolation (drag_debug_*), the
+layer taps, and the end-to-end embeddings against the fp32 oracle / HF BertModel goldens.
+Tolerance: BASELINE.md section 5 -- cosine >= 0.9995 against the fp32 reference."""
+
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import encoder as oenc
+from tests.synth import synth_token_batch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+COS_BAR = 0.9995
+
+
+def _lib():
+    from dial_rag_b200 import _native
+
+    return _native, _native.load()
+
+
+def _bf16(x):
+    return x.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("variant,N,K", [(0, 1152, 384), (1, 1536, 384), (2, 384, 384), (2, 384, 1536), (0, 192, 64)])
+@pytest.mark.parametrize("M", [128, 77, 1000, 20000])
+def test_tcgen05_gemm_vs_torch(variant, N, K, M):
+    native, lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + variant)
+    a = _bf16(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf16(torch.randn(N, K, device="cuda", generator=g) * 0.05)
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    gamma = torch.rand(N, device="cuda", generator=g) + 0.5
+    beta = torch.randn(N, device="cuda", generator=g) * 0.1
+    res = _bf16(torch.randn(M, N, device="cuda", generator=g))
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    stream = torch.cuda.current_stream().cuda_stream
+    native.check(lib.drag_debug_gemm(0, variant, a.data_ptr(), w.data_ptr(), bias.data_ptr(), gamma.data_ptr(),
+                                     beta.data_ptr(), res.data_ptr(), out.data_ptr(), M, N, K, 1e-12, stream))
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().T + bias
+    if variant == 1:
+        ref = torch.nn.functional.gelu(ref)
+    if variant == 2:
+        ref = torch.nn.functional.layer_norm(ref + res.float(), (N,), gamma, beta, 1e-12)
+    got = out.float()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 0.01 * scale + 0.02, (variant, M, N, K, err, scale)
+    # and on average far tighter than the bf16 output rounding bound
+    assert (got - ref).abs().mean().item() <= 0.004 * max(ref.abs().mean().item(), 1e-3) + 1e-3
+
+
+def test_attention_vs_torch():
+    native, lib = _lib()
+    heads, hd = 12, 32
+    lens = [1, 2, 17, 64, 65, 128, 256, 300, 512, 33]
+    cu = np.zeros(len(lens) + 1, dtype=np.int32)
+    cu[1:] = np.cumsum(lens)
+    T = int(cu[-1])
+    g = torch.Generator(device="cuda").manual_seed(5)
+    qkv = _bf16(torch.randn(T, 3 * heads * hd, device="cuda", generator=g) * 1.5)
+    ctx = torch.full((T, heads * hd), float("nan"), device="cuda", dtype=torch.bfloat16)
+    d_cu = torch.from_numpy(cu).cuda()
+    native.check(lib.drag_debug_attention(0, qkv.data_ptr(), ctx.data_ptr(), d_cu.data_ptr(), len(lens), max(lens),
+                                          heads, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    got = ctx.float()
+    assert torch.isfinite(got).all()
+    for i, n in enumerate(lens):
+        blk = qkv[cu[i]:cu[i + 1]].float().view(n, 3, heads, hd)
+        q, k, v = (blk[:, j].permute(1, 0, 2) for j in range(3))
+        p = torch.softmax(q @ k.transpose(1, 2) / math.sqrt(hd), dim=-1)
+        ref = (p @ v).permute(1, 0, 2).reshape(n, heads * hd)
+        err = (got[cu[i]:cu[i + 1]] - ref).abs().max().item()
+        assert err <= 0.03, (n, err)
+
+
+@pytest.fixture(scope="module", params=["hf_init", "stress"])
+def model(request):
+    from dial_rag_b200.embeddings.encoder import B200Encoder
+
+    style = request.param
+    seed = {"hf_init": 0, "stress": 7}[style]
+    w = oenc.synth_weights(seed=seed, style=style)
+    enc = B200Encoder(w, device=0, max_tokens=16384)
+    yield style, w, enc
+    enc.close()
+
+
+def _golden(style):
+    z = np.load(os.path.join(GOLDEN, "encoder_bge.npz"))
+    lens = z[f"{style}:lens"]
+    toks = z[f"{style}:tokens"]
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    return toks.astype(np.int32), cu, z[f"{style}:embeddings"]
+
+
+def _cos(a, b):
+    return (a * b).sum(-1) / (np.linalg.norm(a, axis=-1) * np.linalg.norm(b, axis=-1))
+
+
+def test_layer_taps_vs_oracle(model):
+    style, w, enc = model
+    ids, cu = synth_token_batch(seed=31, n_seq=5, seq_len=200, ragged=True, min_len=5)
+    lists = oenc.packed_to_lists(ids, cu)
+    for layer in (0, 1, 2, 12):
+        got = enc.debug_hidden(ids, cu, layer)
+        shape = oenc.BertShape(layers=layer) if layer else None
+        for i, t in enumerate(lists):
+            tt = torch.tensor([t])
+            if layer == 0:
+                ref = oenc.bert_hidden(w, tt, torch.ones_like(tt), oenc.BertShape(layers=0))[0].numpy()
+            else:
+                ref = oenc.bert_hidden(w, tt, torch.ones_like(tt), shape)[0].numpy()
+            g = got[cu[i]:cu[i + 1]]
+            c = _cos(g, ref)
+            assert c.min() >= (0.99999 if layer == 0 else 0.999), (style, layer, i, float(c.min()))
+            assert np.abs(g - ref).max() <= (0.02 if layer == 0 else 0.15), (style, layer, i)
+
+
+def test_embeddings_vs_hf_golden(model):
+    """cosine >= 0.9995 against HF BertModel fp32 outputs (tests/golden/encoder_bge.npz)."""
+    style, w, enc = model
+    ids, cu, want = _golden(style)
+    got = enc.embed_packed(ids, cu)
+    assert got.shape == want.shape and got.dtype == np.float32
+    np.testing.assert_allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)
+    c = _cos(got, want)
+    assert c.min() >= COS_BAR, (style, c)
+
+
+def test_batch_composition_invariance(model):
+    """An embedding does not depend on what else is in the packed batch."""
+    style, w, enc = model
+    ids, cu, _ = _golden(style)
+    whole = enc.embed_packed(ids, cu)
+    for i in (0, 2, 7):
+        one = enc.embed_packed(ids[cu[i]:cu[i + 1]], np.array([0, cu[i + 1] - cu[i]], dtype=np.int32))
+        assert np.array_equal(one[0], whole[i]), (style, i)
+    order = np.arange(len(cu) - 1)[::-1]
+    lists = oenc.packed_to_lists(ids, cu)
+    rev = enc.embed_token_lists([lists[i] for i in order])
+    assert np.array_equal(rev[::-1], whole)
+
+
+def test_config2_shape_vs_oracle(model):
+    """BASELINE config 2 shape (256-token chunks, all real tokens): oracle on a 64-chunk prefix."""
+    style, w, enc = model
+    ids, cu = synth_token_batch(seed=1, n_seq=64, seq_len=256)
+    got = enc.embed_packed(ids, cu)
+    want = oenc.encode_token_lists(w, oenc.packed_to_lists(ids, cu))
+    assert _cos(got, want).min() >= COS_BAR
+
+
+def test_splits_large_batches_and_truncates(model):
+    style, w, enc = model
+    ids, cu = synth_token_batch(seed=2, n_seq=100, seq_len=256)  # 25600 tokens > max_tokens=16384
+    got = enc.embed_packed(ids, cu)
+    first = enc.embed_packed(ids[: cu[10]], cu[:11])
+    assert np.array_equal(got[:10], first)
+    long = [101] + list(range(1000, 1700)) + [102]  # 702 tokens -> truncated to 512 keeping [SEP]
+    emb = enc.embed_token_lists([long])
+    want = oenc.encode_token_lists(w, [long])
+    assert _cos(emb, want).min() >= COS_BAR
+
+
+def test_invalid_inputs_raise(model):
+    from dial_rag_b200._native import DragError
+
+    style, w, enc = model
+    with pytest.raises(DragError):
+        enc.embed_packed(np.array([101, 102], dtype=np.int32), np.array([0, 0, 2], dtype=np.int32))  # empty sequence
+    with pytest.raises(ValueError):
+        enc.embed_token_lists([[]])

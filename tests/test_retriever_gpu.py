@@ -1,0 +1,89 @@
+"""End-to-end boundary test on the GPU: text -> tokenizer -> CUDA encoder -> index -> retrieval,
+mirroring the reference's tests/test_retrievers.py:44-104 (real-model golden not available
+offline, so the oracle with the same seeded weights provides the expected ranking)."""
+
+import asyncio
+import io
+import os
+
+import numpy as np
+import pytest
+
+from oracle import encoder as oenc
+from oracle import search as osearch
+from tests.text_fixture import CHUNKS, QUERIES, build_vocab_file
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+
+@pytest.fixture(scope="module")
+def stack(tmp_path_factory):
+    from dial_rag_b200.embeddings import embeddings as emb
+    from dial_rag_b200.embeddings.tokenizer import WordPieceTokenizer
+
+    vocab = build_vocab_file(str(tmp_path_factory.mktemp("vocab")))
+    tok = WordPieceTokenizer.from_vocab_file(vocab)
+    w = oenc.synth_weights(seed=7, style="stress")
+    impl = emb.B200BgeEmbeddings(w, tok, device=0, max_tokens=32768)
+    emb.configure(impl)
+    yield emb, tok, w
+    emb.configure(None)
+    impl.client.close()
+
+
+def test_build_index_and_retrieve_matches_oracle(stack):
+    emb, tok, w = stack
+    from dial_rag_b200.records import Chunk
+    from dial_rag_b200.retrievers.semantic_retriever import SemanticRetriever
+
+    class Rec:  # the two DocumentRecord fields from_doc_records touches
+        def __init__(self, embeddings_index):
+            self.embeddings_index = embeddings_index
+
+    docs = [CHUNKS[:40], CHUNKS[40:41], CHUNKS[41:]]
+    stage = io.StringIO()
+    records = []
+    for d in docs:
+        chunks = [Chunk(text=t, metadata={"chunk_id": i}) for i, t in enumerate(d)]
+        multi = asyncio.run(SemanticRetriever.build_index(chunks, stage))
+        assert len(multi) == len(d) and multi[0].embeddings.shape == (1, 384)
+        assert np.asarray(multi[0].embeddings).dtype == np.float32
+        records.append(Rec(multi))
+    assert "Building Semantic indexes started" in stage.getvalue() and "took" in stage.getvalue()
+    records.insert(1, Rec(None))  # a document without an embeddings index is skipped (semantic_retriever.py:30-33)
+    retriever = SemanticRetriever.from_doc_records(records, k=7)
+
+    # oracle: same text preparation + tokenizer, fp32 BERT, reference search
+    def oracle_embed(texts):
+        return oenc.encode_token_lists(w, tok.encode_batch(texts))
+
+    doc_embs = [oracle_embed([oenc.prepare_document_text(t) for t in d]) for d in docs]
+    oracle_docs = [(np.arange(len(e), dtype=np.int64), e) for e in doc_embs]
+    for q in QUERIES:
+        got = retriever._get_relevant_documents(q)
+        got_async = asyncio.run(retriever._aget_relevant_documents(q))
+        assert got == got_async
+        q_emb = oracle_embed([oenc.prepare_query_text(q)])[0].astype(np.float64)
+        want = osearch.find("sqeuclidean_dist", 7, q_emb, oracle_docs)
+        got_pairs = [(d.metadata["doc_id"], d.metadata["chunk_id"]) for d in got]
+        assert all(d.page_content == f"{d.metadata['doc_id']}_{d.metadata['chunk_id']}" for d in got)
+        want_pairs = [(dd, c) for dd, c, _ in want]
+        # embeddings differ at the 1e-3 level (bf16 tensor cores vs fp32): the top hit must agree
+        # and the top-7 sets must overlap almost entirely
+        assert got_pairs[0] == want_pairs[0], (q, got_pairs, want_pairs)
+        assert len(set(got_pairs) & set(want_pairs)) >= 6, (q, got_pairs, want_pairs)
+
+
+def test_embeddings_surface(stack):
+    emb, tok, w = stack
+    assert emb.EMBEDDING_LENGTH == 384
+    vec = emb.bge_embedding.embed_query("what is the climate in the alps?")
+    assert isinstance(vec, list) and len(vec) == 384 and isinstance(vec[0], float)
+    assert abs(np.linalg.norm(vec) - 1.0) < 1e-5
+    rows = asyncio.run(emb.bge_embedding.aembed_documents_numpy(["a\nb", "a b"]))
+    assert rows[0].dtype == np.float32 and rows[0].shape == (384,)
+    assert np.array_equal(rows[0], rows[1])  # newline == space after preparation
+    lists = asyncio.run(emb.bge_embedding.aembed_documents(["hello world"]))
+    assert len(lists) == 1 and len(lists[0]) == 384
+    q_as_doc = emb.bge_embedding.embed_documents([emb.DEFAULT_QUERY_BGE_INSTRUCTION_EN + "hello"])[0]
+    assert np.allclose(q_as_doc, emb.bge_embedding.embed_query("hello"), atol=1e-6)
