@@ -34,10 +34,23 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(smem_row));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src, bool valid) {
   uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
   int sz = valid ? 16 : 0;  // src-size 0 -> zero fill
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(sz) : "memory");
+}
+
+// 2^x for x <= 0 (softmax numerators): one MUFU.EX2, flush-to-zero, no range fix-up code
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -45,10 +58,88 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// One 64-key block of the online softmax for the 16 query rows a warp owns.
+template <bool MASKED>
+__device__ __forceinline__ void attend_block(const __nv_bfloat16* ks, const __nv_bfloat16* vs, int key0, int S,
+                                             const uint32_t (&qa)[2][4], float scale_log2, int lane, float& m_lo,
+                                             float& m_hi, float& l_lo, float& l_hi, float (&o)[4][4]) {
+  const int g = lane >> 2, t = lane & 3;
+      float s[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    // K fragments of 8 keys x 32 dims: four 8x8 blocks (d 0-7, 8-15, 16-23, 24-31) in one ldmatrix
+    uint32_t kf[4];
+    ldmatrix_x4(kf, ks + (size_t)(key0 + nt * 8 + (lane & 7)) * KV_STRIDE + (lane >> 3) * 8);
+    mma_bf16_16816(s[nt], qa[0], kf[0], kf[1]);
+    mma_bf16_16816(s[nt], qa[1], kf[2], kf[3]);
+  }
+  // keys past the end of the sequence exist only in the (peeled) last block
+  if (MASKED) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int key = key0 + nt * 8 + 2 * t;
+      if (key >= S) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+      if (key + 1 >= S) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+    }
+  }
+  float mx_lo = -INFINITY, mx_hi = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    mx_lo = fmaxf(mx_lo, fmaxf(s[nt][0], s[nt][1]));
+    mx_hi = fmaxf(mx_hi, fmaxf(s[nt][2], s[nt][3]));
+  }
+  mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
+  mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+  mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
+  mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+  // key 0 of every sequence is valid, so the running max is finite from the first block on
+  const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);
+  const float corr_lo = fast_exp2((m_lo - mn_lo) * scale_log2), corr_hi = fast_exp2((m_hi - mn_hi) * scale_log2);
+  m_lo = mn_lo;
+  m_hi = mn_hi;
+  const float off_lo = mn_lo * scale_log2, off_hi = mn_hi * scale_log2;
+  float sum_lo = 0.f, sum_hi = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    s[nt][0] = fast_exp2(fmaf(s[nt][0], scale_log2, -off_lo));
+    s[nt][1] = fast_exp2(fmaf(s[nt][1], scale_log2, -off_lo));
+    s[nt][2] = fast_exp2(fmaf(s[nt][2], scale_log2, -off_hi));
+    s[nt][3] = fast_exp2(fmaf(s[nt][3], scale_log2, -off_hi));
+    sum_lo += s[nt][0] + s[nt][1];
+    sum_hi += s[nt][2] + s[nt][3];
+  }
+  l_lo = l_lo * corr_lo + sum_lo;
+  l_hi = l_hi * corr_hi + sum_hi;
+#pragma unroll
+  for (int dt = 0; dt < 4; ++dt) {
+    o[dt][0] *= corr_lo; o[dt][1] *= corr_lo;
+    o[dt][2] *= corr_hi; o[dt][3] *= corr_hi;
+  }
+  // O += P V : P fragments come straight from the score accumulators
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t pa[4];
+    pa[0] = pack2(s[2 * kk][0], s[2 * kk][1]);
+    pa[1] = pack2(s[2 * kk][2], s[2 * kk][3]);
+    pa[2] = pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+    pa[3] = pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+    const int mtx = lane >> 3, r = lane & 7;
+    const __nv_bfloat16* vrow = vs + (size_t)(key0 + kk * 16 + (mtx & 1) * 8 + r) * KV_STRIDE + (mtx >> 1) * 8;
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh) {
+      uint32_t vb[4];
+      ldmatrix_x4_trans(vb, vrow + dh * 16);
+      mma_bf16_16816(o[dh * 2], pa, vb[0], vb[1]);
+      mma_bf16_16816(o[dh * 2 + 1], pa, vb[2], vb[3]);
+    }
+  }
+}
+
 // qkv : [T, 3*hidden] bf16, per token [Q(hidden) | K(hidden) | V(hidden)], head h at columns h*32
 // ctx : [T, hidden] bf16
 // grid = (heads, n_seq), block = WARPS*32, dynamic smem = 2 * round_up(max_len, 64) * 80 bytes
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, 3)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx,
                  const int* __restrict__ cu_seqlens, int hidden, float scale_log2) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
@@ -101,81 +192,11 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
 
-    for (int kb = 0; kb < n_kblocks; ++kb) {
-      const int key0 = kb * 64;
-      float s[8][4];
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-        const __nv_bfloat16* krow = ks + (size_t)(key0 + nt * 8 + g) * KV_STRIDE + 2 * t;
-#pragma unroll
-        for (int ks2 = 0; ks2 < 2; ++ks2) {
-          uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + ks2 * 16);
-          uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + ks2 * 16 + 8);
-          mma_bf16_16816(s[nt], qa[ks2], b0, b1);
-        }
-      }
-      // mask keys past the end of the sequence (only possible in the last block)
-      if (key0 + 64 > S) {
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          const int key = key0 + nt * 8 + 2 * t;
-          if (key >= S) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
-          if (key + 1 >= S) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
-        }
-      }
-      float mx_lo = -INFINITY, mx_hi = -INFINITY;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        mx_lo = fmaxf(mx_lo, fmaxf(s[nt][0], s[nt][1]));
-        mx_hi = fmaxf(mx_hi, fmaxf(s[nt][2], s[nt][3]));
-      }
-      mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
-      mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
-      mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
-      mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
-      // key 0 of every sequence is valid, so the running max is finite from the first block on
-      const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);
-      const float corr_lo = exp2f((m_lo - mn_lo) * scale_log2), corr_hi = exp2f((m_hi - mn_hi) * scale_log2);
-      m_lo = mn_lo;
-      m_hi = mn_hi;
-      const float off_lo = mn_lo * scale_log2, off_hi = mn_hi * scale_log2;
-      float sum_lo = 0.f, sum_hi = 0.f;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        s[nt][0] = exp2f(fmaf(s[nt][0], scale_log2, -off_lo));
-        s[nt][1] = exp2f(fmaf(s[nt][1], scale_log2, -off_lo));
-        s[nt][2] = exp2f(fmaf(s[nt][2], scale_log2, -off_hi));
-        s[nt][3] = exp2f(fmaf(s[nt][3], scale_log2, -off_hi));
-        sum_lo += s[nt][0] + s[nt][1];
-        sum_hi += s[nt][2] + s[nt][3];
-      }
-      l_lo = l_lo * corr_lo + sum_lo;
-      l_hi = l_hi * corr_hi + sum_hi;
-#pragma unroll
-      for (int dt = 0; dt < 4; ++dt) {
-        o[dt][0] *= corr_lo; o[dt][1] *= corr_lo;
-        o[dt][2] *= corr_hi; o[dt][3] *= corr_hi;
-      }
-      // O += P V : P fragments come straight from the score accumulators
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        uint32_t pa[4];
-        pa[0] = pack2(s[2 * kk][0], s[2 * kk][1]);
-        pa[1] = pack2(s[2 * kk][2], s[2 * kk][3]);
-        pa[2] = pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-        pa[3] = pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-        const int mtx = lane >> 3, r = lane & 7;
-        const __nv_bfloat16* vrow = vs + (size_t)(key0 + kk * 16 + (mtx & 1) * 8 + r) * KV_STRIDE + (mtx >> 1) * 8;
-#pragma unroll
-        for (int dh = 0; dh < 2; ++dh) {
-          uint32_t vb[4];
-          ldmatrix_x4_trans(vb, vrow + dh * 16);
-          mma_bf16_16816(o[dh * 2], pa, vb[0], vb[1]);
-          mma_bf16_16816(o[dh * 2 + 1], pa, vb[2], vb[3]);
-        }
-      }
-    }
+    const int n_full = S >> 6;  // blocks with 64 valid keys
+    for (int kb = 0; kb < n_full; ++kb)
+      attend_block<false>(ks, vs, kb * 64, S, qa, scale_log2, lane, m_lo, m_hi, l_lo, l_hi, o);
+    if (n_full < n_kblocks)
+      attend_block<true>(ks, vs, n_full * 64, S, qa, scale_log2, lane, m_lo, m_hi, l_lo, l_hi, o);
     l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
     l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
     l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);

@@ -6,8 +6,10 @@
 // cu_seqlens marks their boundaries, so padded positions cost nothing and the attention
 // mask is implicit.
 //
-// Per forward:  embed+LN  ->  12 x { QKV GEMM | attention | out-proj GEMM + residual + LN |
-//               FFN-up GEMM + GELU | FFN-down GEMM + residual + LN }  ->  CLS + 2x L2 normalise.
+// Per forward:  embed (raw sum + row statistics)  ->  12 x { QKV GEMM | attention | out-proj GEMM +
+//               residual | FFN-up GEMM + GELU | FFN-down GEMM + residual }  ->  CLS LayerNorm + 2x L2
+//               normalise.  LayerNorms are folded into the GEMMs (see drag_gemm.cuh): hidden states
+//               are stored raw (pre-LN, bf16) with per-row (sum, sum^2) partials.
 // All GEMMs are the tcgen05/TMA kernel of drag_gemm.cuh with fused epilogues.
 #include <mutex>
 #include <new>
@@ -24,8 +26,10 @@ using bf16 = __nv_bfloat16;
 
 constexpr int HIDDEN = 384;
 constexpr int HEAD_DIM = 32;
-constexpr int QKV_BLOCK_N = 192;
-constexpr int FFN_BLOCK_N = 256;
+constexpr int QKV_BLOCK_N = 192;   // 1152 = 6 x 192
+constexpr int FFN_BLOCK_N = 256;   // 1536 = 6 x 256
+constexpr int RES_BLOCK_N = 128;   // 384 = 3 x 128 (one statistics slot per tile)
+constexpr int PARTS = gemm::STATS_PARTS;
 
 // ---------------------------------------------------------------------------------
 // small kernels
@@ -36,13 +40,13 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// X[t] = LayerNorm(word[ids[t]] + pos[t - start(seq(t))] + type[0]); one warp per token,
+// x_raw[t] = word[ids[t]] + pos[t - start(seq(t))] + type[0] (bf16) and the row's (sum, sum^2);
+// the embedding LayerNorm itself is folded into the first QKV GEMM / residual.  One warp per token,
 // each lane owns 12 of the 384 features (3 x float4, coalesced).
 __global__ void __launch_bounds__(256)
-embed_ln_kernel(const int* __restrict__ ids, const int* __restrict__ cu_seqlens, int n_seq, int total,
-                const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type0,
-                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int vocab,
-                bf16* __restrict__ out, float* __restrict__ out_f32) {
+embed_kernel(const int* __restrict__ ids, const int* __restrict__ cu_seqlens, int n_seq, int total,
+             const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type0,
+             int vocab, bf16* __restrict__ out, float2* __restrict__ stats) {
   const int tok = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (tok >= total) return;
@@ -54,53 +58,64 @@ embed_ln_kernel(const int* __restrict__ ids, const int* __restrict__ cu_seqlens,
   const int p = tok - cu_seqlens[lo];
   int id = ids[tok];
   id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
-  float v[12];
-  float s = 0.f;
+  float s = 0.f, ss = 0.f;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const int e = c * 128 + lane * 4;
     float4 w = __ldg(reinterpret_cast<const float4*>(word + (size_t)id * HIDDEN + e));
     float4 pp = __ldg(reinterpret_cast<const float4*>(pos + (size_t)p * HIDDEN + e));
     float4 tt = __ldg(reinterpret_cast<const float4*>(type0 + e));
-    v[c * 4 + 0] = w.x + pp.x + tt.x; v[c * 4 + 1] = w.y + pp.y + tt.y;
-    v[c * 4 + 2] = w.z + pp.z + tt.z; v[c * 4 + 3] = w.w + pp.w + tt.w;
-    s += v[c * 4] + v[c * 4 + 1] + v[c * 4 + 2] + v[c * 4 + 3];
+    const float v0 = w.x + pp.x + tt.x, v1 = w.y + pp.y + tt.y, v2 = w.z + pp.z + tt.z, v3 = w.w + pp.w + tt.w;
+    s += (v0 + v1) + (v2 + v3);
+    ss = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, ss))));
+    *reinterpret_cast<uint2*>(out + (size_t)tok * HIDDEN + e) = make_uint2(gemm::pack_bf16(v0, v1), gemm::pack_bf16(v2, v3));
   }
-  const float mean = warp_sum(s) * (1.f / HIDDEN);
-  float ss = 0.f;
-#pragma unroll
-  for (int i = 0; i < 12; ++i) { float d = v[i] - mean; ss = fmaf(d, d, ss); }
-  const float rstd = rsqrtf(warp_sum(ss) * (1.f / HIDDEN) + eps);
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const int e = c * 128 + lane * 4;
-    float4 g = __ldg(reinterpret_cast<const float4*>(gamma + e));
-    float4 b = __ldg(reinterpret_cast<const float4*>(beta + e));
-    float y0 = (v[c * 4 + 0] - mean) * rstd * g.x + b.x, y1 = (v[c * 4 + 1] - mean) * rstd * g.y + b.y;
-    float y2 = (v[c * 4 + 2] - mean) * rstd * g.z + b.z, y3 = (v[c * 4 + 3] - mean) * rstd * g.w + b.w;
-    uint2 packed = make_uint2(gemm::pack_bf16(y0, y1), gemm::pack_bf16(y2, y3));
-    *reinterpret_cast<uint2*>(out + (size_t)tok * HIDDEN + e) = packed;
-    if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)tok * HIDDEN + e) = make_float4(y0, y1, y2, y3);
-  }
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  if (lane < PARTS) stats[(size_t)tok * PARTS + lane] = lane == 0 ? make_float2(s, ss) : make_float2(0.f, 0.f);
 }
 
-// out[s] = normalize(normalize(X[cu[s]]))  -- CLS pooling + the two F.normalize(p=2, eps=1e-12)
-__global__ void __launch_bounds__(256)
-pool_normalize_kernel(const bf16* __restrict__ x, const int* __restrict__ cu_seqlens, int n_seq, float* __restrict__ out) {
-  const int seq = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (seq >= n_seq) return;
-  const bf16* row = x + (size_t)cu_seqlens[seq] * HIDDEN;
-  float v[12];
-  float ss = 0.f;
+__device__ __forceinline__ void load_row12(const bf16* row, int lane, float (&v)[12]) {
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     uint2 raw = *reinterpret_cast<const uint2*>(row + c * 128 + lane * 4);
     v[c * 4 + 0] = __uint_as_float(raw.x << 16); v[c * 4 + 1] = __uint_as_float(raw.x & 0xffff0000u);
     v[c * 4 + 2] = __uint_as_float(raw.y << 16); v[c * 4 + 3] = __uint_as_float(raw.y & 0xffff0000u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) ss = fmaf(v[c * 4 + i], v[c * 4 + i], ss);
   }
+}
+
+__device__ __forceinline__ void apply_ln12(float (&v)[12], int lane, const float2* stats, size_t row,
+                                           const float* gamma, const float* beta, float eps) {
+  float s = 0.f, ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < PARTS; ++i) { float2 p = stats[row * PARTS + i]; s += p.x; ss += p.y; }
+  const float mu = s * (1.f / HIDDEN);
+  const float rstd = rsqrtf(fmaxf(ss * (1.f / HIDDEN) - mu * mu, 0.f) + eps);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c * 128 + lane * 4));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c * 128 + lane * 4));
+    v[c * 4 + 0] = (v[c * 4 + 0] - mu) * rstd * g.x + b.x; v[c * 4 + 1] = (v[c * 4 + 1] - mu) * rstd * g.y + b.y;
+    v[c * 4 + 2] = (v[c * 4 + 2] - mu) * rstd * g.z + b.z; v[c * 4 + 3] = (v[c * 4 + 3] - mu) * rstd * g.w + b.w;
+  }
+}
+
+// out[s] = normalize(normalize(LN(x_raw[cu[s]])))  -- final LayerNorm of the CLS row, CLS pooling and
+// the two F.normalize(p=2, eps=1e-12)
+__global__ void __launch_bounds__(256)
+pool_normalize_kernel(const bf16* __restrict__ x, const float2* __restrict__ stats, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, float eps, const int* __restrict__ cu_seqlens, int n_seq,
+                      float* __restrict__ out) {
+  const int seq = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (seq >= n_seq) return;
+  const size_t row = (size_t)cu_seqlens[seq];
+  float v[12];
+  load_row12(x + row * HIDDEN, lane, v);
+  apply_ln12(v, lane, stats, row, gamma, beta, eps);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) ss = fmaf(v[i], v[i], ss);
   float inv = 1.f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
   ss = 0.f;
 #pragma unroll
@@ -110,6 +125,22 @@ pool_normalize_kernel(const bf16* __restrict__ x, const int* __restrict__ cu_seq
   for (int c = 0; c < 3; ++c)
     *reinterpret_cast<float4*>(out + (size_t)seq * HIDDEN + c * 128 + lane * 4) =
         make_float4(v[c * 4] * inv, v[c * 4 + 1] * inv, v[c * 4 + 2] * inv, v[c * 4 + 3] * inv);
+}
+
+// debug tap: hidden[t] = LN(x_raw[t]) as fp32 (what HF's BertModel exposes as a layer output)
+__global__ void __launch_bounds__(256)
+ln_apply_kernel(const bf16* __restrict__ x, const float2* __restrict__ stats, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float eps, int total, float* __restrict__ out) {
+  const int tok = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (tok >= total) return;
+  float v[12];
+  load_row12(x + (size_t)tok * HIDDEN, lane, v);
+  apply_ln12(v, lane, stats, (size_t)tok, gamma, beta, eps);
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    *reinterpret_cast<float4*>(out + (size_t)tok * HIDDEN + c * 128 + lane * 4) =
+        make_float4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
 }
 
 __global__ void bf16_to_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, size_t n) {
@@ -148,6 +179,7 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 // bf16 row-major [rows, cols] -> TMA map with a (box_rows x 64) box and 128-byte swizzle
+// (loads: 128 x 64 A tiles / BLOCK_N x 64 W tiles; stores: 32 x 64 epilogue tiles)
 static int make_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return fail(DRAG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
@@ -163,9 +195,12 @@ static int make_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
 }
 
 struct Layer {
-  bf16 *w_qkv, *w_o, *w_up, *w_down;           // [1152,384] [384,384] [1536,384] [384,1536]
-  float *b_qkv, *b_o, *b_up, *b_down;
-  float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  bf16 *w_qkv, *w_o, *w_up, *w_down;   // [1152,384] (gamma_in folded) [384,384] [1536,384] (gamma_1 folded) [384,1536]
+  float *qkv_c, *qkv_d;                // folded LN_in terms of the QKV projection   [1152]
+  float *up_c, *up_d;                  // folded LN_1 terms of the FFN up projection [1536]
+  float *o_cold, *o_gamma;             // out-proj residual: b_o + beta_in, gamma_in [384]
+  float *down_cold, *down_gamma;       // FFN-down residual: b_down + beta_1, gamma_1 [384]
+  float *ln2_g, *ln2_b;                // this layer's output LayerNorm (used by the taps / the pooler)
   CUtensorMap tm_qkv, tm_o, tm_up, tm_down;
 };
 
@@ -184,9 +219,11 @@ struct drag_encoder {
   std::vector<void*> allocs;
   float *word = nullptr, *pos = nullptr, *type0 = nullptr, *emb_g = nullptr, *emb_b = nullptr;
   std::vector<Layer> layers;
-  // activations (bf16)
+  // activations (bf16): x / y are RAW (pre-LayerNorm) hidden states with their row statistics
   bf16 *x = nullptr, *y = nullptr, *qkv = nullptr, *ctx = nullptr, *h = nullptr;
-  CUtensorMap tm_x, tm_y, tm_ctx, tm_h;
+  float2 *stats_x = nullptr, *stats_y = nullptr;  // [T][PARTS] partial (sum, sum^2)
+  CUtensorMap tm_x, tm_y, tm_ctx, tm_h;           // A-operand loads (128 x 64 boxes)
+  CUtensorMap ts_x, ts_y, ts_qkv, ts_h;           // epilogue stores (32 x 64 boxes)
   // host-buffer path
   cudaStream_t stream = nullptr;
   int32_t *d_ids = nullptr, *d_cu = nullptr;
@@ -194,6 +231,29 @@ struct drag_encoder {
   int32_t *p_ids = nullptr, *p_cu = nullptr;
   float* p_out = nullptr;
   int64_t out_cap = 0;
+  // optional per-kernel-class timing (bench.py roofline): event pairs recorded around launches
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;  // start/stop pairs
+  std::vector<int> prof_class;
+  size_t prof_used = 0;
+};
+
+enum KernelClass { KC_EMBED = 0, KC_GEMM_QKV, KC_ATTENTION, KC_GEMM_OUT_LN, KC_GEMM_UP_GELU, KC_GEMM_DOWN_LN, KC_POOL, KC_COUNT };
+
+struct ProfScope {
+  drag_encoder* e;
+  cudaStream_t st;
+  cudaEvent_t stop = nullptr;
+  ProfScope(drag_encoder* enc, int klass, cudaStream_t s) : e(enc), st(s) {
+    if (!e->profiling || e->prof_used + 2 > e->prof_events.size()) return;
+    cudaEventRecord(e->prof_events[e->prof_used], st);
+    stop = e->prof_events[e->prof_used + 1];
+    e->prof_class.push_back(klass);
+    e->prof_used += 2;
+  }
+  ~ProfScope() {
+    if (stop) cudaEventRecord(stop, st);
+  }
 };
 
 namespace {
@@ -240,9 +300,11 @@ int upload_concat_f32(drag_encoder* e, float** dst, std::initializer_list<const 
 }
 
 template <int BLOCK_N, int EPI, int EPI_WARPS, int STAGES>
-int launch_gemm(const drag_encoder* e, const CUtensorMap& ta, const CUtensorMap& tw, const gemm::GemmParams& p, cudaStream_t st) {
+int launch_gemm(const drag_encoder* e, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tout,
+                const gemm::GemmParams& p, cudaStream_t st) {
   auto kern = gemm::gemm_kernel<BLOCK_N, EPI, EPI_WARPS, STAGES>;
-  constexpr size_t smem = gemm::smem_bytes<BLOCK_N, STAGES>();
+  constexpr size_t smem = gemm::smem_bytes<BLOCK_N, STAGES, EPI_WARPS>();
+  static_assert(smem <= 227 * 1024, "GEMM configuration exceeds the 227 KB shared memory of an SM");
   static std::once_flag once[16];
   static cudaError_t attr_err[16];
   const int dev_slot = e->device & 15;
@@ -254,10 +316,15 @@ int launch_gemm(const drag_encoder* e, const CUtensorMap& ta, const CUtensorMap&
   const int m_tiles = (p.M + gemm::BLOCK_M - 1) / gemm::BLOCK_M;
   const int tiles = m_tiles * (p.N / BLOCK_N);
   const int grid = tiles < e->sms ? tiles : e->sms;
-  kern<<<grid, 64 + 32 * EPI_WARPS, smem, st>>>(ta, tw, p);
+  kern<<<grid, 64 + 32 * EPI_WARPS, smem, st>>>(ta, tw, tout, p);
   DRAG_CUDA_OK(cudaGetLastError());
   return DRAG_OK;
 }
+
+// the four GEMM configurations of a layer
+#define DRAG_GEMM_QKV  launch_gemm<QKV_BLOCK_N, gemm::EPI_LNIN, 4, 4>
+#define DRAG_GEMM_UP   launch_gemm<FFN_BLOCK_N, gemm::EPI_LNIN_GELU, 8, 3>
+#define DRAG_GEMM_RES  launch_gemm<RES_BLOCK_N, gemm::EPI_RES, 8, 5>
 
 int forward_impl(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu, const int32_t* h_cu, int n_seq,
                  float* d_out, int stop_after_layer, float* d_hidden, cudaStream_t st) {
@@ -277,11 +344,11 @@ int forward_impl(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu, con
 
   const bool tap = d_hidden != nullptr;
   {
+    ProfScope prof(e, KC_EMBED, st);
     const int warps_per_block = 8;
     const int blocks = (total + warps_per_block - 1) / warps_per_block;
-    embed_ln_kernel<<<blocks, warps_per_block * 32, 0, st>>>(d_ids, d_cu, n_seq, total, e->word, e->pos, e->type0, e->emb_g,
-                                                            e->emb_b, sh.ln_eps, sh.vocab, e->x,
-                                                            (tap && stop_after_layer == 0) ? d_hidden : nullptr);
+    embed_kernel<<<blocks, warps_per_block * 32, 0, st>>>(d_ids, d_cu, n_seq, total, e->word, e->pos, e->type0, sh.vocab,
+                                                         e->x, e->stats_x);
     DRAG_CUDA_OK(cudaGetLastError());
   }
   const int n_layers = (tap && stop_after_layer < sh.layers) ? stop_after_layer : sh.layers;
@@ -293,33 +360,100 @@ int forward_impl(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu, con
     gemm::GemmParams p{};
     p.M = total;
     p.ln_eps = sh.ln_eps;
-    // QKV projection
-    p.N = 3 * HIDDEN; p.K = HIDDEN; p.bias = L.b_qkv; p.out = e->qkv;
-    int rc = launch_gemm<QKV_BLOCK_N, gemm::EPI_BIAS, 4, 4>(e, e->tm_x, L.tm_qkv, p, st);
+    p.inv_width = 1.0f / HIDDEN;
+    int rc;
+    // QKV projection of LN_in(x): qkv = rstd*(x_raw . (gamma (.) Wqkv)^T - mu*c) + d
+    p.N = 3 * HIDDEN; p.K = HIDDEN; p.colc = L.qkv_c; p.cold = L.qkv_d; p.in_stats = e->stats_x;
+    {
+      ProfScope prof(e, KC_GEMM_QKV, st);
+      rc = DRAG_GEMM_QKV(e, e->tm_x, L.tm_qkv, e->ts_qkv, p, st);
+    }
     if (rc) return rc;
     // attention
-    attn::attention_kernel<<<dim3(sh.heads, n_seq), attn::WARPS * 32, attn_smem, st>>>(e->qkv, e->ctx, d_cu, HIDDEN, scale_log2);
+    {
+      ProfScope prof(e, KC_ATTENTION, st);
+      attn::attention_kernel<<<dim3(sh.heads, n_seq), attn::WARPS * 32, attn_smem, st>>>(e->qkv, e->ctx, d_cu, HIDDEN, scale_log2);
+    }
     DRAG_CUDA_OK(cudaGetLastError());
-    // output projection + residual + LayerNorm
-    p.N = HIDDEN; p.K = HIDDEN; p.bias = L.b_o; p.gamma = L.ln1_g; p.beta = L.ln1_b; p.residual = e->x; p.out = e->y;
-    rc = launch_gemm<HIDDEN, gemm::EPI_BIAS_RES_LN, 8, 3>(e, e->tm_ctx, L.tm_o, p, st);
+    // y_raw = ctx . Wo^T + b_o + LN_in(x_raw)   (+ row statistics of y_raw)
+    p.N = HIDDEN; p.K = HIDDEN; p.colc = nullptr; p.cold = L.o_cold; p.gamma = L.o_gamma; p.in_stats = e->stats_x;
+    p.residual = e->x; p.out_stats = e->stats_y;
+    {
+      ProfScope prof(e, KC_GEMM_OUT_LN, st);
+      rc = DRAG_GEMM_RES(e, e->tm_ctx, L.tm_o, e->ts_y, p, st);
+    }
     if (rc) return rc;
-    // FFN up + GELU
-    p.N = sh.inter; p.K = HIDDEN; p.bias = L.b_up; p.gamma = nullptr; p.beta = nullptr; p.residual = nullptr; p.out = e->h;
-    rc = launch_gemm<FFN_BLOCK_N, gemm::EPI_BIAS_GELU, 8, 4>(e, e->tm_y, L.tm_up, p, st);
+    // h = gelu(LN_1(y) . W1^T + b_1)
+    p.N = sh.inter; p.K = HIDDEN; p.colc = L.up_c; p.cold = L.up_d; p.gamma = nullptr; p.in_stats = e->stats_y;
+    p.residual = nullptr; p.out_stats = nullptr;
+    {
+      ProfScope prof(e, KC_GEMM_UP_GELU, st);
+      rc = DRAG_GEMM_UP(e, e->tm_y, L.tm_up, e->ts_h, p, st);
+    }
     if (rc) return rc;
-    // FFN down + residual + LayerNorm
-    p.N = HIDDEN; p.K = sh.inter; p.bias = L.b_down; p.gamma = L.ln2_g; p.beta = L.ln2_b; p.residual = e->y; p.out = e->x;
-    p.out_f32 = (tap && l + 1 == n_layers) ? d_hidden : nullptr;
-    rc = launch_gemm<HIDDEN, gemm::EPI_BIAS_RES_LN, 8, 3>(e, e->tm_h, L.tm_down, p, st);
+    // x_raw = h . W2^T + b_2 + LN_1(y_raw)   (+ row statistics of x_raw); LN_2 is applied by the consumers
+    p.N = HIDDEN; p.K = sh.inter; p.colc = nullptr; p.cold = L.down_cold; p.gamma = L.down_gamma; p.in_stats = e->stats_y;
+    p.residual = e->y; p.out_stats = e->stats_x;
+    {
+      ProfScope prof(e, KC_GEMM_DOWN_LN, st);
+      rc = DRAG_GEMM_RES(e, e->tm_h, L.tm_down, e->ts_x, p, st);
+    }
     if (rc) return rc;
   }
+  // LayerNorm that turns the current raw hidden state into the model's hidden state
+  const float* fin_g = n_layers == 0 ? e->emb_g : e->layers[n_layers - 1].ln2_g;
+  const float* fin_b = n_layers == 0 ? e->emb_b : e->layers[n_layers - 1].ln2_b;
+  if (tap) {
+    ln_apply_kernel<<<(total + 7) / 8, 256, 0, st>>>(e->x, e->stats_x, fin_g, fin_b, sh.ln_eps, total, d_hidden);
+    DRAG_CUDA_OK(cudaGetLastError());
+  }
   if (d_out) {
+    ProfScope prof(e, KC_POOL, st);
     const int blocks = (n_seq + 7) / 8;
-    pool_normalize_kernel<<<blocks, 256, 0, st>>>(e->x, d_cu, n_seq, d_out);
+    pool_normalize_kernel<<<blocks, 256, 0, st>>>(e->x, e->stats_x, fin_g, fin_b, sh.ln_eps, d_cu, n_seq, d_out);
     DRAG_CUDA_OK(cudaGetLastError());
   }
   return DRAG_OK;
+}
+
+// W' = bf16(W (.) gamma) [N, K];  c_n = sum_k W'_nk;  d_n = sum_k beta_k W_nk + bias_n
+int upload_folded(drag_encoder* e, bf16** w_dev, float** c_dev, float** d_dev, std::initializer_list<const float*> ws,
+                  std::initializer_list<const float*> biases, size_t rows_each, size_t K, const float* gamma, const float* beta) {
+  const size_t n_total = rows_each * ws.size();
+  std::vector<uint16_t> wq(n_total * K);
+  std::vector<float> c(n_total), d(n_total);
+  size_t r0 = 0;
+  auto bias_it = biases.begin();
+  for (const float* w : ws) {
+    const float* b = *bias_it++;
+    for (size_t r = 0; r < rows_each; ++r) {
+      double cs = 0.0, ds = 0.0;
+      for (size_t k = 0; k < K; ++k) {
+        const float wf = w[r * K + k];
+        const uint16_t q = f32_to_bf16_rne(wf * gamma[k]);
+        wq[(r0 + r) * K + k] = q;
+        uint32_t u = (uint32_t)q << 16;
+        float qf;
+        memcpy(&qf, &u, 4);
+        cs += (double)qf;
+        ds += (double)beta[k] * (double)wf;
+      }
+      c[r0 + r] = (float)cs;
+      d[r0 + r] = (float)(ds + (double)b[r]);
+    }
+    r0 += rows_each;
+  }
+  int rc = dev_alloc(e, w_dev, wq.size());
+  if (rc) return rc;
+  DRAG_CUDA_OK(cudaMemcpy(*w_dev, wq.data(), wq.size() * 2, cudaMemcpyHostToDevice));
+  if ((rc = upload_f32(e, c_dev, c.data(), c.size()))) return rc;
+  return upload_f32(e, d_dev, d.data(), d.size());
+}
+
+int upload_sum_f32(drag_encoder* e, float** dst, const float* a, const float* b, size_t n) {
+  std::vector<float> tmp(n);
+  for (size_t i = 0; i < n; ++i) tmp[i] = a[i] + b[i];
+  return upload_f32(e, dst, tmp.data(), n);
 }
 
 }  // namespace
@@ -331,6 +465,7 @@ extern "C" int drag_encoder_create(const drag_bert_shape* shape, const float* co
   DRAG_REQUIRE(shape->hidden == HIDDEN, "drag_encoder_create: this build supports hidden=384 (got %d)", shape->hidden);
   DRAG_REQUIRE(shape->heads * HEAD_DIM == shape->hidden, "drag_encoder_create: head_dim must be 32");
   DRAG_REQUIRE(shape->inter % FFN_BLOCK_N == 0 && shape->inter % gemm::BLOCK_K == 0, "drag_encoder_create: intermediate size must be a multiple of 256");
+  static_assert(HIDDEN / RES_BLOCK_N == PARTS, "one statistics slot per residual-GEMM column tile");
   DRAG_REQUIRE(shape->layers >= 1 && shape->vocab >= 1 && shape->max_pos >= 1 && shape->max_pos <= 512, "drag_encoder_create: bad shape");
   DRAG_REQUIRE(n_tensors == 5 + 16 * shape->layers, "drag_encoder_create: expected %d tensors, got %d", 5 + 16 * shape->layers, n_tensors);
   DRAG_REQUIRE(max_tokens >= 1 && max_tokens <= (1ll << 30), "drag_encoder_create: bad max_tokens");
@@ -359,23 +494,26 @@ extern "C" int drag_encoder_create(const drag_bert_shape* shape, const float* co
   e->layers.resize(shape->layers);
   for (int l = 0; l < shape->layers; ++l) {
     const float* const* t = h_tensors + 5 + 16 * l;
+    // LayerNorm feeding this layer: the embedding LN for layer 0, else the previous layer's output LN
+    const float* g_in = l == 0 ? h_tensors[3] : h_tensors[5 + 16 * (l - 1) + 14];
+    const float* b_in = l == 0 ? h_tensors[4] : h_tensors[5 + 16 * (l - 1) + 15];
+    const float* g_1 = t[12];  // attention.output.LayerNorm
+    const float* b_1 = t[13];
     Layer& L = e->layers[l];
-    if ((rc = upload_bf16(e, &L.w_qkv, {t[0], t[2], t[4]}, H, H))) return bail(rc);
-    if ((rc = upload_concat_f32(e, &L.b_qkv, {t[1], t[3], t[5]}, H))) return bail(rc);
+    if ((rc = upload_folded(e, &L.w_qkv, &L.qkv_c, &L.qkv_d, {t[0], t[2], t[4]}, {t[1], t[3], t[5]}, H, H, g_in, b_in))) return bail(rc);
     if ((rc = upload_bf16(e, &L.w_o, {t[6]}, H, H))) return bail(rc);
-    if ((rc = upload_f32(e, &L.b_o, t[7], H))) return bail(rc);
-    if ((rc = upload_bf16(e, &L.w_up, {t[8]}, F, H))) return bail(rc);
-    if ((rc = upload_f32(e, &L.b_up, t[9], F))) return bail(rc);
+    if ((rc = upload_sum_f32(e, &L.o_cold, t[7], b_in, H))) return bail(rc);
+    if ((rc = upload_f32(e, &L.o_gamma, g_in, H))) return bail(rc);
+    if ((rc = upload_folded(e, &L.w_up, &L.up_c, &L.up_d, {t[8]}, {t[9]}, F, H, g_1, b_1))) return bail(rc);
     if ((rc = upload_bf16(e, &L.w_down, {t[10]}, H, F))) return bail(rc);
-    if ((rc = upload_f32(e, &L.b_down, t[11], H))) return bail(rc);
-    if ((rc = upload_f32(e, &L.ln1_g, t[12], H))) return bail(rc);
-    if ((rc = upload_f32(e, &L.ln1_b, t[13], H))) return bail(rc);
+    if ((rc = upload_sum_f32(e, &L.down_cold, t[11], b_1, H))) return bail(rc);
+    if ((rc = upload_f32(e, &L.down_gamma, g_1, H))) return bail(rc);
     if ((rc = upload_f32(e, &L.ln2_g, t[14], H))) return bail(rc);
     if ((rc = upload_f32(e, &L.ln2_b, t[15], H))) return bail(rc);
-    if ((rc = make_tmap(&L.tm_qkv, L.w_qkv, 3 * H, H, gemm::Cfg<QKV_BLOCK_N>::UMMA_N))) return bail(rc);
-    if ((rc = make_tmap(&L.tm_o, L.w_o, H, H, gemm::Cfg<HIDDEN>::UMMA_N))) return bail(rc);
-    if ((rc = make_tmap(&L.tm_up, L.w_up, F, H, gemm::Cfg<FFN_BLOCK_N>::UMMA_N))) return bail(rc);
-    if ((rc = make_tmap(&L.tm_down, L.w_down, H, F, gemm::Cfg<HIDDEN>::UMMA_N))) return bail(rc);
+    if ((rc = make_tmap(&L.tm_qkv, L.w_qkv, 3 * H, H, QKV_BLOCK_N))) return bail(rc);
+    if ((rc = make_tmap(&L.tm_o, L.w_o, H, H, RES_BLOCK_N))) return bail(rc);
+    if ((rc = make_tmap(&L.tm_up, L.w_up, F, H, FFN_BLOCK_N))) return bail(rc);
+    if ((rc = make_tmap(&L.tm_down, L.w_down, H, F, RES_BLOCK_N))) return bail(rc);
   }
   const size_t T = (size_t)e->max_tokens;
   if ((rc = dev_alloc(e, &e->x, T * H))) return bail(rc);
@@ -383,13 +521,20 @@ extern "C" int drag_encoder_create(const drag_bert_shape* shape, const float* co
   if ((rc = dev_alloc(e, &e->ctx, T * H))) return bail(rc);
   if ((rc = dev_alloc(e, &e->qkv, T * 3 * H))) return bail(rc);
   if ((rc = dev_alloc(e, &e->h, T * F))) return bail(rc);
+  if ((rc = dev_alloc(e, &e->stats_x, T * PARTS))) return bail(rc);
+  if ((rc = dev_alloc(e, &e->stats_y, T * PARTS))) return bail(rc);
   // activations are zeroed once so that the tail rows of the last 128-row tile hold finite values
   cudaMemset(e->x, 0, T * H * 2); cudaMemset(e->y, 0, T * H * 2); cudaMemset(e->ctx, 0, T * H * 2);
   cudaMemset(e->qkv, 0, T * 3 * H * 2); cudaMemset(e->h, 0, T * F * 2);
+  cudaMemset(e->stats_x, 0, T * PARTS * 8); cudaMemset(e->stats_y, 0, T * PARTS * 8);
   if ((rc = make_tmap(&e->tm_x, e->x, T, H, gemm::BLOCK_M))) return bail(rc);
   if ((rc = make_tmap(&e->tm_y, e->y, T, H, gemm::BLOCK_M))) return bail(rc);
   if ((rc = make_tmap(&e->tm_ctx, e->ctx, T, H, gemm::BLOCK_M))) return bail(rc);
   if ((rc = make_tmap(&e->tm_h, e->h, T, F, gemm::BLOCK_M))) return bail(rc);
+  if ((rc = make_tmap(&e->ts_x, e->x, T, H, gemm::STORE_ROWS))) return bail(rc);
+  if ((rc = make_tmap(&e->ts_y, e->y, T, H, gemm::STORE_ROWS))) return bail(rc);
+  if ((rc = make_tmap(&e->ts_qkv, e->qkv, T, 3 * H, gemm::STORE_ROWS))) return bail(rc);
+  if ((rc = make_tmap(&e->ts_h, e->h, T, F, gemm::STORE_ROWS))) return bail(rc);
 
   // host-buffer path: pinned staging + device mirrors
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(DRAG_ERR_CUDA, "cudaStreamCreate failed"));
@@ -409,6 +554,7 @@ extern "C" int drag_encoder_destroy(drag_encoder* e) {
   if (!e) return DRAG_OK;
   DeviceGuard guard(e->device);
   if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
+  for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
   for (void* p : e->allocs) cudaFree(p);
   if (e->p_ids) cudaFreeHost(e->p_ids);
   if (e->p_cu) cudaFreeHost(e->p_cu);
@@ -479,10 +625,11 @@ extern "C" int drag_encoder_embed_host(drag_encoder* e, const int32_t* h_ids, co
 // ---------------------------------------------------------------------------------
 // kernel-level entry points used by the parity tests to check each fused kernel in isolation
 // ---------------------------------------------------------------------------------
-extern "C" int drag_debug_gemm(int device, int variant, const void* d_a, const void* d_w, const float* d_bias,
-                               const float* d_gamma, const float* d_beta, const void* d_residual, void* d_out,
-                               int M, int N, int K, float ln_eps, void* stream) {
-  DRAG_REQUIRE(d_a && d_w && d_bias && d_out && M >= 1, "drag_debug_gemm: null pointer / empty problem");
+extern "C" int drag_debug_gemm(int device, int variant, const void* d_a, const void* d_w, const float* d_colc,
+                               const float* d_cold, const float* d_gamma, const void* d_in_stats, const void* d_residual,
+                               void* d_out, void* d_out_stats, int M, int N, int K, float inv_width, float ln_eps,
+                               void* stream) {
+  DRAG_REQUIRE(d_a && d_w && d_cold && d_in_stats && d_out && M >= 1, "drag_debug_gemm: null pointer / empty problem");
   DRAG_REQUIRE(K % gemm::BLOCK_K == 0 && K >= gemm::BLOCK_K, "drag_debug_gemm: K must be a multiple of 64");
   DeviceGuard guard(device);
   if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_debug_gemm: cannot select device %d", device);
@@ -490,25 +637,26 @@ extern "C" int drag_debug_gemm(int device, int variant, const void* d_a, const v
   fake.device = device;
   fake.sms = sm_count(device);
   gemm::GemmParams p{};
-  p.M = M; p.N = N; p.K = K; p.bias = d_bias; p.gamma = d_gamma; p.beta = d_beta; p.ln_eps = ln_eps;
-  p.residual = (const bf16*)d_residual; p.out = (bf16*)d_out;
-  CUtensorMap ta, tw;
+  p.M = M; p.N = N; p.K = K; p.colc = d_colc; p.cold = d_cold; p.gamma = d_gamma; p.in_stats = (const float2*)d_in_stats;
+  p.inv_width = inv_width; p.ln_eps = ln_eps; p.residual = (const bf16*)d_residual; p.out_stats = (float2*)d_out_stats;
+  CUtensorMap ta, tw, tout;
   int rc = make_tmap(&ta, d_a, (uint64_t)M, (uint64_t)K, gemm::BLOCK_M);
   if (rc) return rc;
+  if ((rc = make_tmap(&tout, d_out, (uint64_t)M, (uint64_t)N, gemm::STORE_ROWS))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   switch (variant) {
     case 0:
-      DRAG_REQUIRE(N % QKV_BLOCK_N == 0, "drag_debug_gemm: N must be a multiple of %d", QKV_BLOCK_N);
-      if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, gemm::Cfg<QKV_BLOCK_N>::UMMA_N))) return rc;
-      return launch_gemm<QKV_BLOCK_N, gemm::EPI_BIAS, 4, 4>(&fake, ta, tw, p, st);
+      DRAG_REQUIRE(N % QKV_BLOCK_N == 0 && d_colc, "drag_debug_gemm: variant 0 needs N %% %d == 0 and colc", QKV_BLOCK_N);
+      if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, QKV_BLOCK_N))) return rc;
+      return DRAG_GEMM_QKV(&fake, ta, tw, tout, p, st);
     case 1:
-      DRAG_REQUIRE(N % FFN_BLOCK_N == 0, "drag_debug_gemm: N must be a multiple of %d", FFN_BLOCK_N);
-      if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, gemm::Cfg<FFN_BLOCK_N>::UMMA_N))) return rc;
-      return launch_gemm<FFN_BLOCK_N, gemm::EPI_BIAS_GELU, 8, 4>(&fake, ta, tw, p, st);
+      DRAG_REQUIRE(N % FFN_BLOCK_N == 0 && d_colc, "drag_debug_gemm: variant 1 needs N %% %d == 0 and colc", FFN_BLOCK_N);
+      if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, FFN_BLOCK_N))) return rc;
+      return DRAG_GEMM_UP(&fake, ta, tw, tout, p, st);
     case 2:
-      DRAG_REQUIRE(N == HIDDEN && d_gamma && d_beta && d_residual, "drag_debug_gemm: LN variant needs N=384, gamma, beta, residual");
-      if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, gemm::Cfg<HIDDEN>::UMMA_N))) return rc;
-      return launch_gemm<HIDDEN, gemm::EPI_BIAS_RES_LN, 8, 3>(&fake, ta, tw, p, st);
+      DRAG_REQUIRE(N == HIDDEN && d_gamma && d_residual && d_out_stats, "drag_debug_gemm: variant 2 needs N=384, gamma, residual, out_stats");
+      if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, RES_BLOCK_N))) return rc;
+      return DRAG_GEMM_RES(&fake, ta, tw, tout, p, st);
     default:
       return fail(DRAG_ERR_INVALID, "drag_debug_gemm: unknown variant %d", variant);
   }
@@ -527,5 +675,40 @@ extern "C" int drag_debug_attention(int device, const void* d_qkv, void* d_ctx, 
   attn::attention_kernel<<<dim3(heads, n_seq), attn::WARPS * 32, smem, (cudaStream_t)stream>>>(
       (const bf16*)d_qkv, (bf16*)d_ctx, d_cu_seqlens, heads * HEAD_DIM, scale_log2);
   DRAG_CUDA_OK(cudaGetLastError());
+  return DRAG_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// per-kernel-class device timing for bench.py's roofline (CUDA events on the launch stream)
+// ---------------------------------------------------------------------------------
+extern "C" int drag_encoder_profile_begin(drag_encoder* e, int max_launches) {
+  DRAG_REQUIRE(e && max_launches >= 1 && max_launches <= (1 << 20), "drag_encoder_profile_begin: bad arguments");
+  std::lock_guard<std::mutex> hold(e->lock);
+  DeviceGuard guard(e->device);
+  while (e->prof_events.size() < (size_t)max_launches * 2) {
+    cudaEvent_t ev;
+    DRAG_CUDA_OK(cudaEventCreate(&ev));
+    e->prof_events.push_back(ev);
+  }
+  e->prof_class.clear();
+  e->prof_used = 0;
+  e->profiling = true;
+  return DRAG_OK;
+}
+
+// ms_by_class / launches_by_class: arrays of 7 (embed, gemm_qkv, attention, gemm_out_ln, gemm_up_gelu,
+// gemm_down_ln, pool).  The caller must have synchronised the stream(s) the forwards ran on.
+extern "C" int drag_encoder_profile_end(drag_encoder* e, double* ms_by_class, int* launches_by_class) {
+  DRAG_REQUIRE(e && ms_by_class && launches_by_class, "drag_encoder_profile_end: null pointer");
+  std::lock_guard<std::mutex> hold(e->lock);
+  DeviceGuard guard(e->device);
+  e->profiling = false;
+  for (int i = 0; i < KC_COUNT; ++i) { ms_by_class[i] = 0.0; launches_by_class[i] = 0; }
+  for (size_t i = 0; i < e->prof_class.size(); ++i) {
+    float ms = 0.f;
+    DRAG_CUDA_OK(cudaEventElapsedTime(&ms, e->prof_events[2 * i], e->prof_events[2 * i + 1]));
+    ms_by_class[e->prof_class[i]] += ms;
+    launches_by_class[e->prof_class[i]] += 1;
+  }
   return DRAG_OK;
 }

@@ -1,21 +1,28 @@
 // Persistent warp-specialised tcgen05 GEMM with fused epilogues for the BERT encoder
-// (SURVEY.md 8a row a5):   OUT[M, N] = epilogue( A[M, K] . W[N, K]^T + bias )
+// (SURVEY.md 8a row a5):   OUT[M, N] = epilogue( A[M, K] . W[N, K]^T )
 //
 //   A  : bf16 activations, row-major [M, K]          (K-major operand)
-//   W  : bf16 weights exactly as HF stores them, [N, K] row-major (K-major operand)
-//   acc: fp32 in TMEM
+//   W  : bf16 weights as HF stores them, [N, K] row-major (K-major operand)
+//   acc: fp32 in TMEM, double buffered (2 x BLOCK_N <= 512 columns)
+//
+// LayerNorm is FOLDED into the GEMMs instead of being a pass of its own.  Activations are kept
+// "raw" (pre-LayerNorm, bf16) together with per-row partial sums (sum v, sum v^2); for a consumer
+// GEMM whose input is LN(v) = (v - mu) * rstd * gamma + beta we use
+//     LN(v) . W^T = rstd * ( v . (gamma (.) W)^T  -  mu * c ) + d,
+//     c_n = sum_k (gamma (.) W)_nk,   d_n = sum_k beta_k W_nk + bias_n,
+// i.e. the tensor cores multiply the raw rows by gamma-scaled weights and the epilogue applies
+// the per-row (mu, rstd) and per-column (c, d) terms.  Epilogues:
+//     EPI_LNIN       out = rstd*(acc - mu*c) + d                               (QKV projection)
+//     EPI_LNIN_GELU  out = gelu(rstd*(acc - mu*c) + d)                         (FFN up)
+//     EPI_RES        out = acc + cold + LN(residual_raw)  (raw, pre-LN) and the row's partial
+//                    (sum, sum^2) over this tile's columns -> out_stats   (attention out / FFN down)
 //
 // CTA = 2 + EPI_WARPS warps, one CTA per SM, looping over 128 x BLOCK_N output tiles:
-//   warp 0   TMA producer: cp.async.bulk.tensor loads of the A tile (128 x 64) and the W tile
-//            (BLOCK_N x 64) into a STAGES-deep 128B-swizzled shared-memory ring
-//   warp 1   MMA issuer: one thread issues tcgen05.mma (M=128, N=BLOCK_N or 2 x BLOCK_N/2, K=16)
-//            per 16-wide k-step; tcgen05.commit releases ring slots / publishes the accumulator
-//   warps 2+ epilogue: tcgen05.ld the accumulator (thread = one row, 32 columns at a time) and
-//            apply   EPI_BIAS          -> +bias                              (QKV projection)
-//                    EPI_BIAS_GELU     -> +bias, erf-GELU                    (FFN up)
-//                    EPI_BIAS_RES_LN   -> +bias +residual, LayerNorm over the full 384-wide row
-//            then store bf16.  With 2*BLOCK_N <= 512 TMEM columns the accumulator is double
-//            buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warp 0   TMA producer (cp.async.bulk.tensor, 128B swizzle) into a STAGES-deep smem ring
+//   warp 1   MMA issuer: one thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) per k-step;
+//            tcgen05.commit releases ring slots / publishes the accumulator
+//   warps 2+ epilogue: tcgen05.ld (thread = one row, 32 columns at a time) -> math -> bf16 ->
+//            128B-swizzled staging tile in smem -> TMA store (coalesced, no LSU scatter)
 #pragma once
 
 #include <cuda_bf16.h>
@@ -29,40 +36,52 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int STATS_PARTS = 3;          // partial (sum, sum^2) slots per row
+constexpr int STORE_COLS = 64;          // columns per TMA store box (128 bytes of bf16)
+constexpr int STORE_ROWS = 32;          // rows per TMA store box (one epilogue warp)
+constexpr int STAGING_BYTES = STORE_ROWS * STORE_COLS * 2;  // 4 KB per epilogue warp
 
-enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RES_LN = 2 };
+enum { EPI_LNIN = 0, EPI_LNIN_GELU = 1, EPI_RES = 2 };
 
 struct GemmParams {
   int M, N, K;                     // M = valid rows (tokens)
-  const float* bias;               // [N]
-  const float* gamma;              // [N]  (LN epilogue)
-  const float* beta;               // [N]
+  const float* colc;               // [N] LNIN: c_n
+  const float* cold;               // [N] LNIN: d_n ; RES: bias_n + beta_n (beta of the residual's LN)
+  const float* gamma;              // [N] RES: gamma of the residual's LN
+  const float2* in_stats;          // [M][STATS_PARTS] partial sums of the rows the LN applies to
+                                   //   (LNIN: the A rows, RES: the residual rows)
+  float inv_width;                 // 1 / (feature width the LN statistics run over)
   float ln_eps;
-  const __nv_bfloat16* residual;   // [M, N] (LN epilogue)
-  __nv_bfloat16* out;              // [M, N]
-  float* out_f32;                  // optional fp32 copy of the output (debug taps), may be null
+  const __nv_bfloat16* residual;   // [M, N] raw residual rows (RES)
+  float2* out_stats;               // [M][STATS_PARTS] (RES): slot n_blk of every row
 };
 
 template <int BLOCK_N>
 struct Cfg {
-  static constexpr int UMMA_N = BLOCK_N > 256 ? BLOCK_N / 2 : BLOCK_N;
-  static constexpr int N_SPLIT = BLOCK_N / UMMA_N;
-  static constexpr int ACC_STAGES = (2 * BLOCK_N <= 512) ? 2 : 1;
-  static constexpr int TMEM_COLS = (ACC_STAGES * BLOCK_N <= 128) ? 128 : (ACC_STAGES * BLOCK_N <= 256 ? 256 : 512);
+  static constexpr int ACC_STAGES = 2;
+  static constexpr int TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static_assert(UMMA_N % 16 == 0 && UMMA_N >= 16 && UMMA_N <= 256, "invalid UMMA N");
+  static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "invalid UMMA N");
+  static_assert(2 * BLOCK_N <= 512, "accumulator must double-buffer in 512 TMEM columns");
   static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024-byte alignment");
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int EPI_WARPS>
 constexpr size_t smem_bytes() {
-  // ring + barriers/tmem pointer/LN partials + slack for manual 1024-byte alignment
-  return (size_t)STAGES * Cfg<BLOCK_N>::STAGE_BYTES + 4096 + 1024;
+  // ring + per-warp store staging + barriers/tmem pointer + slack for manual 1024-byte alignment
+  return (size_t)STAGES * Cfg<BLOCK_N>::STAGE_BYTES + (size_t)EPI_WARPS * STAGING_BYTES + 2048 + 1024;
 }
 
-__device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+// GELU(x) = x * Phi(x) with Phi(x) ~ 0.5 * (1 + tanh(x * (c0 + c1 x^2 + c2 x^4))): minimax fit on
+// [-8, 8] (max abs error 2.5e-5 vs the erf form, far below the bf16 output rounding); one MUFU.TANH.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float x2 = fminf(x * x, 64.0f);
+  const float p = fmaf(fmaf(-0.00035152308f, x2, 0.03700567580f), x2, 0.79750785923f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * p));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -70,25 +89,40 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// per-row LayerNorm statistics from the partial sums
+__device__ __forceinline__ void row_stats(const float2* stats, int row, bool ok, float inv_width, float eps, float& mu, float& rstd) {
+  float s = 0.f, ss = 0.f;
+  if (ok) {
+#pragma unroll
+    for (int i = 0; i < STATS_PARTS; ++i) {
+      float2 p = __ldg(stats + (size_t)row * STATS_PARTS + i);
+      s += p.x;
+      ss += p.y;
+    }
+  }
+  mu = s * inv_width;
+  rstd = rsqrtf(fmaxf(ss * inv_width - mu * mu, 0.f) + eps);
+}
+
 template <int BLOCK_N, int EPI, int EPI_WARPS, int STAGES>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+            const __grid_constant__ CUtensorMap tmap_out, GemmParams p) {
   using C = Cfg<BLOCK_N>;
   static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "epilogue uses 4 or 8 warps");
   constexpr int COL_GROUPS = EPI_WARPS / 4;
   constexpr int COLS_PER_THREAD = BLOCK_N / COL_GROUPS;
-  static_assert(COLS_PER_THREAD % 32 == 0, "epilogue works in 32-column chunks");
-  static_assert(EPI != EPI_BIAS_RES_LN || C::ACC_STAGES == 1, "LN epilogue rewrites the accumulator in place");
+  static_assert(COLS_PER_THREAD % STORE_COLS == 0, "epilogue stores 64-column groups");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * C::STAGE_BYTES);
+  uint8_t* staging = smem + (size_t)STAGES * C::STAGE_BYTES;  // 1024-aligned, 4 KB per epilogue warp
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + (size_t)EPI_WARPS * STAGING_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  float2* ln_part = reinterpret_cast<float2*>(tmem_ptr_smem + 4);  // [COL_GROUPS][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -100,6 +134,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmap_a);
     tc::tma_prefetch_desc(&tmap_w);
+    tc::tma_prefetch_desc(&tmap_out);
     for (int s = 0; s < STAGES; ++s) {
       tc::mbar_init(&full_bar[s], 1);
       tc::mbar_init(&empty_bar[s], 1);
@@ -129,13 +164,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         for (int kb = 0; kb < k_blocks; ++kb) {
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = ring + (size_t)stage * C::STAGE_BYTES;
-          uint8_t* b_dst = a_dst + A_STAGE_BYTES;
           tc::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           tc::tma_load_2d(&tmap_a, &full_bar[stage], a_dst, kb * BLOCK_K, m_blk * BLOCK_M);
-#pragma unroll
-          for (int h = 0; h < C::N_SPLIT; ++h)
-            tc::tma_load_2d(&tmap_w, &full_bar[stage], b_dst + (size_t)h * C::UMMA_N * BLOCK_K * 2, kb * BLOCK_K,
-                            n_blk * BLOCK_N + h * C::UMMA_N);
+          tc::tma_load_2d(&tmap_w, &full_bar[stage], a_dst + A_STAGE_BYTES, kb * BLOCK_K, n_blk * BLOCK_N);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -144,7 +175,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::umma_idesc_bf16(BLOCK_M, C::UMMA_N);
+      constexpr uint32_t idesc = tc::umma_idesc_bf16(BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -157,17 +188,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           tc::mbar_wait(&full_bar[stage], phase);
           tc::tc_fence_after();
           const uint32_t a_addr = tc::smem_u32(ring + (size_t)stage * C::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
           const uint64_t a_desc = tc::umma_desc_sw128(a_addr);
+          const uint64_t b_desc = tc::umma_desc_sw128(a_addr + A_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-#pragma unroll
-            for (int h = 0; h < C::N_SPLIT; ++h) {
-              const uint64_t b_desc = tc::umma_desc_sw128(b_addr + (uint32_t)(h * C::UMMA_N * BLOCK_K * 2));
-              // +32 bytes per 16-element k-step inside the 128-byte swizzle row (encoded >> 4)
-              tc::umma_bf16(d_tmem + (uint32_t)(h * C::UMMA_N), a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2),
-                            idesc, (kb | k) != 0 ? 1u : 0u);
-            }
+            // +32 bytes per 16-element k-step inside the 128-byte swizzle row (encoded >> 4)
+            tc::umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
           }
           tc::umma_commit(&empty_bar[stage]);  // ring slot reusable once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -183,6 +209,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int quarter = warp & 3;           // TMEM lanes this warp may touch: [32*quarter, +32)
     const int col_group = ew >> 2;
     const int row_in_tile = quarter * 32 + lane;
+    uint8_t* stage_buf = staging + (size_t)ew * STAGING_BYTES;
+    const uint32_t stage_row = tc::smem_u32(stage_buf) + (uint32_t)lane * 128u;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -190,92 +218,85 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int row = m_blk * BLOCK_M + row_in_tile;
       const bool row_ok = row < p.M;
       const int col0 = n_blk * BLOCK_N + col_group * COLS_PER_THREAD;
+      float mu, rstd;
+      row_stats(p.in_stats, row, row_ok, p.inv_width, p.ln_eps, mu, rstd);
+      float s_sum = 0.f, s_sq = 0.f;
+
       tc::mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + col_group * COLS_PER_THREAD);
-      __nv_bfloat16* out_row = p.out + (size_t)row * p.N + col0;
 
-      if (EPI == EPI_BIAS_RES_LN) {
-        const __nv_bfloat16* res_row = p.residual + (size_t)row * p.N + col0;
-        float s = 0.f, ss = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < COLS_PER_THREAD; c += 32) {
+      for (int g = 0; g < COLS_PER_THREAD; g += STORE_COLS) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int c = g + half * 32;
           uint32_t r[32];
           tc::tmem_ld32(t_row + c, r);
-          uint4 rv[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            rv[i] = row_ok ? __ldg(reinterpret_cast<const uint4*>(res_row + c) + i) : make_uint4(0, 0, 0, 0);
-          tc::tmem_ld_wait();
-          const uint32_t* rw = reinterpret_cast<const uint32_t*>(rv);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float r0 = __uint_as_float(rw[i] << 16), r1 = __uint_as_float(rw[i] & 0xffff0000u);
-            float v0 = __uint_as_float(r[2 * i]) + __ldg(p.bias + col0 + c + 2 * i) + r0;
-            float v1 = __uint_as_float(r[2 * i + 1]) + __ldg(p.bias + col0 + c + 2 * i + 1) + r1;
-            s += v0 + v1;
-            ss = fmaf(v0, v0, fmaf(v1, v1, ss));
-            r[2 * i] = __float_as_uint(v0);
-            r[2 * i + 1] = __float_as_uint(v1);
-          }
-          tc::tmem_st32(t_row + c, r);
-        }
-        tc::tmem_st_wait();
-        if (COL_GROUPS > 1) {
-          ln_part[col_group * 128 + row_in_tile] = make_float2(s, ss);
-          asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-          float2 o = ln_part[(col_group ^ 1) * 128 + row_in_tile];
-          s += o.x;
-          ss += o.y;
-        }
-        const float inv_n = 1.0f / (float)BLOCK_N;
-        const float mean = s * inv_n;
-        const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + p.ln_eps);
-#pragma unroll 1
-        for (int c = 0; c < COLS_PER_THREAD; c += 32) {
-          uint32_t r[32];
-          tc::tmem_ld32(t_row + c, r);
-          tc::tmem_ld_wait();
           uint32_t o[16];
+          if (EPI == EPI_RES) {
+            uint4 rv[4];
+            const uint4* res = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.N + col0 + c);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int cc = col0 + c + 2 * i;
-            float v0 = (__uint_as_float(r[2 * i]) - mean) * rstd * __ldg(p.gamma + cc) + __ldg(p.beta + cc);
-            float v1 = (__uint_as_float(r[2 * i + 1]) - mean) * rstd * __ldg(p.gamma + cc + 1) + __ldg(p.beta + cc + 1);
-            o[i] = pack_bf16(v0, v1);
-            if (p.out_f32 && row_ok) {
-              p.out_f32[(size_t)row * p.N + cc] = v0;
-              p.out_f32[(size_t)row * p.N + cc + 1] = v1;
+            for (int i = 0; i < 4; ++i) rv[i] = row_ok ? __ldg(res + i) : make_uint4(0, 0, 0, 0);
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(rv);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + c) + i);
+              const float4 cd = __ldg(reinterpret_cast<const float4*>(p.cold + col0 + c) + i);
+              const float g4[4] = {ga.x, ga.y, ga.z, ga.w};
+              const float d4[4] = {cd.x, cd.y, cd.z, cd.w};
+              float v[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int e = 4 * i + j;
+                const uint32_t w = rw[e >> 1];
+                const float res_raw = (e & 1) ? __uint_as_float(w & 0xffff0000u) : __uint_as_float(w << 16);
+                const float a = g4[j] * rstd;
+                v[j] = fmaf(res_raw - mu, a, __uint_as_float(r[e]) + d4[j]);
+                s_sum += v[j];
+                s_sq = fmaf(v[j], v[j], s_sq);
+              }
+              o[2 * i] = pack_bf16(v[0], v[1]);
+              o[2 * i + 1] = pack_bf16(v[2], v[3]);
+            }
+          } else {
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 cc = __ldg(reinterpret_cast<const float4*>(p.colc + col0 + c) + i);
+              const float4 cd = __ldg(reinterpret_cast<const float4*>(p.cold + col0 + c) + i);
+              const float c4[4] = {cc.x, cc.y, cc.z, cc.w};
+              const float d4[4] = {cd.x, cd.y, cd.z, cd.w};
+              float v[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                v[j] = fmaf(rstd, fmaf(-mu, c4[j], __uint_as_float(r[4 * i + j])), d4[j]);
+                if (EPI == EPI_LNIN_GELU) v[j] = gelu_fast(v[j]);
+              }
+              o[2 * i] = pack_bf16(v[0], v[1]);
+              o[2 * i + 1] = pack_bf16(v[2], v[3]);
             }
           }
-          if (row_ok) {
+          if (half == 0) {
+            // the previous TMA store of this warp must have finished reading the staging tile
+            if (lane == 0) tc::tma_store_wait_read();
+            __syncwarp();
+          }
+          // 128B-swizzled row: 16-byte chunk j of row r lives at chunk (j ^ (r & 7))
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              reinterpret_cast<uint4*>(out_row + c)[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t chunk = (uint32_t)((half * 4 + j) ^ (lane & 7));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + chunk * 16u), "r"(o[4 * j]),
+                         "r"(o[4 * j + 1]), "r"(o[4 * j + 2]), "r"(o[4 * j + 3]) : "memory");
           }
         }
-        if (COL_GROUPS > 1) asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");  // ln_part reusable
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < COLS_PER_THREAD; c += 32) {
-          uint32_t r[32];
-          tc::tmem_ld32(t_row + c, r);
-          tc::tmem_ld_wait();
-          uint32_t o[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int cc = col0 + c + 2 * i;
-            float v0 = __uint_as_float(r[2 * i]) + __ldg(p.bias + cc);
-            float v1 = __uint_as_float(r[2 * i + 1]) + __ldg(p.bias + cc + 1);
-            if (EPI == EPI_BIAS_GELU) { v0 = gelu_erf(v0); v1 = gelu_erf(v1); }
-            o[i] = pack_bf16(v0, v1);
-          }
-          if (row_ok) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              reinterpret_cast<uint4*>(out_row + c)[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-          }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tc::tma_store_2d(&tmap_out, stage_buf, col0 + g, m_blk * BLOCK_M + quarter * 32);
+          tc::tma_store_commit();
         }
       }
       // all TMEM reads of this warp are complete -> hand the accumulator back to the MMA warp
@@ -283,7 +304,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[acc]);
       if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+
+      if (EPI == EPI_RES) {
+        if (COL_GROUPS == 1) {
+          if (row_ok) p.out_stats[(size_t)row * STATS_PARTS + n_blk] = make_float2(s_sum, s_sq);
+        } else {
+          // two warps share a row (column halves): combine through shared memory in a fixed order
+          float2* part = reinterpret_cast<float2*>(tmem_ptr_smem + 4);  // [128]
+          if (col_group == 1) part[row_in_tile] = make_float2(s_sum, s_sq);
+          asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+          if (col_group == 0 && row_ok) {
+            const float2 o2 = part[row_in_tile];
+            p.out_stats[(size_t)row * STATS_PARTS + n_blk] = make_float2(s_sum + o2.x, s_sq + o2.y);
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+        }
+      }
     }
+    if (lane == 0) tc::tma_store_wait_all();
   }
 
   tc::tc_fence_before();

@@ -54,6 +54,8 @@ _SIGNATURES = {
     "drag_encoder_forward": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P]),
     "drag_encoder_embed_host": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "drag_encoder_forward_debug": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
+    "drag_encoder_profile_begin": (C.c_int, [_P, C.c_int]),
+    "drag_encoder_profile_end": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "drag_row_sqnorm": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int, _P, _P]),
     "drag_distances": (C.c_int, [C.c_int, _P, C.c_int, C.c_int64, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
     "drag_topk_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
@@ -64,7 +66,8 @@ _SIGNATURES = {
     ),
     "drag_topk_merge": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "drag_rows_to_chunks": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, _P, _P, _P]),
-    "drag_debug_gemm": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
+    "drag_debug_gemm": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int,
+                                  C.c_float, C.c_float, _P]),
     "drag_debug_attention": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
 }
 

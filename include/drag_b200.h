@@ -115,6 +115,15 @@ int drag_encoder_forward_debug(drag_encoder* enc, const int32_t* d_ids, const in
                                const int32_t* h_cu_seqlens, int n_seq, int stop_after_layer,
                                float* d_hidden, void* stream);
 
+/*
+ * Per-kernel-class device timing (CUDA events on the launch stream) for roofline reporting.
+ * _begin arms up to max_launches event pairs; _end (after the caller synchronised the stream)
+ * returns summed milliseconds and launch counts for the 7 classes
+ *   {embed+LN, QKV GEMM, attention, out-proj GEMM+LN, FFN-up GEMM+GELU, FFN-down GEMM+LN, pool}.
+ */
+int drag_encoder_profile_begin(drag_encoder* enc, int max_launches);
+int drag_encoder_profile_end(drag_encoder* enc, double* ms_by_class, int* launches_by_class);
+
 /* ------------------------------------------------------------------------- *
  *  Index: row norms + exact top-k                                            *
  *  replaces ENUM_TO_METRIC[...] + np.argsort(kind="stable")[:limit] of       *
@@ -184,13 +193,17 @@ int drag_rows_to_chunks(const int64_t* d_rows, int64_t n, const int64_t* d_doc_o
  * ------------------------------------------------------------------------- */
 
 /*
- * OUT[M,N] = epilogue(A[M,K] . W[N,K]^T + bias), bf16 in/out, fp32 accumulate (tcgen05).
- *   variant 0: +bias (QKV projection, N % 192 == 0)     1: +bias, erf-GELU (N % 256 == 0)
- *   variant 2: +bias +residual, LayerNorm(gamma, beta, ln_eps) over N == 384
+ * OUT[M,N] = epilogue(A[M,K] . W[N,K]^T), bf16 in/out, fp32 accumulate (tcgen05), LayerNorm folded:
+ * with (mu, rstd) of a row taken from d_in_stats ([M][3] float2 partial (sum, sum^2), width 1/inv_width)
+ *   variant 0: out = rstd*(acc - mu*colc) + cold                       (N % 192 == 0)
+ *   variant 1: out = gelu(rstd*(acc - mu*colc) + cold)                 (N % 256 == 0)
+ *   variant 2: out = acc + cold + (residual - mu)*rstd*gamma, and the row's per-128-column-tile
+ *              (sum, sum^2) of `out` -> d_out_stats [M][3]             (N == 384)
  */
-int drag_debug_gemm(int device, int variant, const void* d_a, const void* d_w, const float* d_bias,
-                    const float* d_gamma, const float* d_beta, const void* d_residual, void* d_out,
-                    int M, int N, int K, float ln_eps, void* stream);
+int drag_debug_gemm(int device, int variant, const void* d_a, const void* d_w, const float* d_colc,
+                    const float* d_cold, const float* d_gamma, const void* d_in_stats, const void* d_residual,
+                    void* d_out, void* d_out_stats, int M, int N, int K, float inv_width, float ln_eps,
+                    void* stream);
 
 /* ctx[T, heads*32] = softmax(Q K^T / sqrt(32)) V per packed sequence; d_qkv is bf16 [T, 3*heads*32]. */
 int drag_debug_attention(int device, const void* d_qkv, void* d_ctx, const int32_t* d_cu_seqlens,

@@ -28,34 +28,61 @@ def _bf16(x):
     return x.to(torch.bfloat16)
 
 
+def _row_stats(x, parts=3):
+    """[M][3] float2 partial (sum, sum^2) of the rows of x, split unevenly over the 3 slots."""
+    xf = x.float()
+    M, W = xf.shape
+    cuts = [0, W // 3, W // 3 + 7, W]
+    out = torch.zeros(M, parts, 2, device=x.device)
+    for i in range(parts):
+        blk = xf[:, cuts[i]:cuts[i + 1]]
+        out[:, i, 0] = blk.sum(1)
+        out[:, i, 1] = (blk * blk).sum(1)
+    return out.contiguous()
+
+
 @pytest.mark.parametrize("variant,N,K", [(0, 1152, 384), (1, 1536, 384), (2, 384, 384), (2, 384, 1536), (0, 192, 64)])
 @pytest.mark.parametrize("M", [128, 77, 1000, 20000])
 def test_tcgen05_gemm_vs_torch(variant, N, K, M):
+    """Each fused GEMM epilogue (LayerNorm folded, see drag_gemm.cuh) against plain torch fp32."""
     native, lib = _lib()
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N + variant)
-    a = _bf16(torch.randn(M, K, device="cuda", generator=g))
+    a = _bf16(torch.randn(M, K, device="cuda", generator=g) + 0.3)
     w = _bf16(torch.randn(N, K, device="cuda", generator=g) * 0.05)
-    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    colc = torch.randn(N, device="cuda", generator=g) * 0.2
+    cold = torch.randn(N, device="cuda", generator=g) * 0.1
     gamma = torch.rand(N, device="cuda", generator=g) + 0.5
-    beta = torch.randn(N, device="cuda", generator=g) * 0.1
-    res = _bf16(torch.randn(M, N, device="cuda", generator=g))
+    res = _bf16(torch.randn(M, N, device="cuda", generator=g) * 2 + 0.5)
+    eps = 1e-12
+    normed = res if variant == 2 else a  # rows the folded LayerNorm statistics describe
+    stats = _row_stats(normed)
+    width = normed.shape[1]
+    mu = normed.float().mean(1, keepdim=True)
+    rstd = torch.rsqrt(normed.float().var(1, unbiased=False, keepdim=True) + eps)
     out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    out_stats = torch.full((M, 3, 2), float("nan"), device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
-    native.check(lib.drag_debug_gemm(0, variant, a.data_ptr(), w.data_ptr(), bias.data_ptr(), gamma.data_ptr(),
-                                     beta.data_ptr(), res.data_ptr(), out.data_ptr(), M, N, K, 1e-12, stream))
+    native.check(lib.drag_debug_gemm(0, variant, a.data_ptr(), w.data_ptr(), colc.data_ptr(), cold.data_ptr(),
+                                     gamma.data_ptr(), stats.data_ptr(), res.data_ptr(), out.data_ptr(),
+                                     out_stats.data_ptr(), M, N, K, 1.0 / width, eps, stream))
     torch.cuda.synchronize()
-    ref = a.float() @ w.float().T + bias
-    if variant == 1:
-        ref = torch.nn.functional.gelu(ref)
+    acc = a.float() @ w.float().T
     if variant == 2:
-        ref = torch.nn.functional.layer_norm(ref + res.float(), (N,), gamma, beta, 1e-12)
+        ref = acc + cold + (res.float() - mu) * rstd * gamma
+    else:
+        ref = rstd * (acc - mu * colc) + cold
+        if variant == 1:
+            ref = torch.nn.functional.gelu(ref)
     got = out.float()
     assert torch.isfinite(got).all()
     err = (got - ref).abs().max().item()
     scale = ref.abs().max().item()
     assert err <= 0.01 * scale + 0.02, (variant, M, N, K, err, scale)
-    # and on average far tighter than the bf16 output rounding bound
     assert (got - ref).abs().mean().item() <= 0.004 * max(ref.abs().mean().item(), 1e-3) + 1e-3
+    if variant == 2:
+        want = torch.stack([torch.stack((ref[:, i * 128:(i + 1) * 128].sum(1), (ref[:, i * 128:(i + 1) * 128] ** 2).sum(1)), 1)
+                            for i in range(3)], 1)
+        assert torch.allclose(out_stats, want, rtol=2e-4, atol=2e-2), (out_stats - want).abs().max()
 
 
 def test_attention_vs_torch():
@@ -123,7 +150,7 @@ def test_layer_taps_vs_oracle(model):
             g = got[cu[i]:cu[i + 1]]
             c = _cos(g, ref)
             assert c.min() >= (0.99999 if layer == 0 else 0.999), (style, layer, i, float(c.min()))
-            assert np.abs(g - ref).max() <= (0.02 if layer == 0 else 0.15), (style, layer, i)
+            assert np.abs(g - ref).max() <= (0.03 if layer == 0 else 0.15), (style, layer, i)
 
 
 def test_embeddings_vs_hf_golden(model):
