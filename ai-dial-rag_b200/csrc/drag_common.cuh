@@ -1,6 +1,7 @@
 // Shared helpers for the drag_b200 C-ABI library (sm_100a only).
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -41,6 +42,11 @@ struct DeviceGuard {
 };
 
 int sm_count(int device);
+
+// bf16 row-major [rows, cols] -> TMA map with a (box_rows x 64 columns) box and the 128-byte swizzle
+// (out-of-bounds rows/columns read as zero and are clipped on stores).  The driver entry point
+// cuTensorMapEncodeTiled is resolved at run time, so libcuda is not a link-time dependency.
+int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 

@@ -19,6 +19,7 @@
 // Ordering is lexicographic on (key, row id): ascending distance, ties -> lowest row id,
 // NaN last -- exactly what a stable argsort over the concatenated matrix yields.
 #include "drag_common.cuh"
+#include "drag_topk_tc.cuh"
 
 namespace drag {
 namespace topk {
@@ -729,6 +730,196 @@ static size_t carve(const Plan& p, int n_queries, void* base, Workspace* ws) {
   return off;
 }
 
+
+// ---------------------------------------------------------------------------------
+// batched path (drag_topk_tc.cuh): exact float64 re-rank of the surviving candidates.
+// One CTA per query; a warp scores one candidate row with the arithmetic of scan_vec_kernel
+// (same element order, same xor-shuffle reduction => bit-identical float64 scores), then the
+// CTA sorts (key, row) in shared memory and writes the first k.
+// ---------------------------------------------------------------------------------
+struct RerankArgs {
+  const void* mat;
+  long long n_rows;
+  int dim;
+  const float* row_sq;
+  const double* queries;
+  const double* q_sq;
+  const double* q_norm;
+  const uint2* cand;
+  const int* cnt;
+  const int* overflow;
+  int cap, k;
+  long long row_base;
+  double* out_dist;
+  long long* out_row;
+  int* out_count;
+  int* out_status;
+};
+
+constexpr int RERANK_WARPS = 8;
+
+template <typename T, int NCH, int METRIC>
+__global__ void __launch_bounds__(RERANK_WARPS * 32) rerank_kernel(RerankArgs a) {
+  constexpr int EPV = RowVec<T>::EPV;
+  __shared__ uint64_t skeys[tcs::RERANK_MAX];
+  __shared__ uint32_t srows[tcs::RERANK_MAX];
+  __shared__ int s_bad;
+  const int q = blockIdx.x;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const T* mat = reinterpret_cast<const T*>(a.mat);
+  const int m = a.cnt[q];
+  const long long want_ll = a.n_rows < (long long)a.k ? a.n_rows : (long long)a.k;
+  const int want = (int)want_ll;
+  if (threadIdx.x == 0) s_bad = 0;
+  if (a.overflow[q] || m > tcs::RERANK_MAX || m < want) {
+    if (threadIdx.x == 0) { a.out_status[q] = 1; a.out_count[q] = 0; }
+    return;
+  }
+  __syncthreads();
+  double qreg[NCH * EPV];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int j = 0; j < EPV; ++j) {
+      const int e = c * 32 * EPV + lane * EPV + j;
+      qreg[c * EPV + j] = e < a.dim ? a.queries[(size_t)q * a.dim + e] : 0.0;
+    }
+  const double qsq = a.q_sq[q], qnorm = a.q_norm[q];
+  const uint2* mine = a.cand + (size_t)q * a.cap;
+  for (int i = warp; i < m; i += RERANK_WARPS) {
+    const uint32_t row = mine[i].y;
+    double acc = 0.0, nn = 0.0;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int e = c * 32 * EPV + lane * EPV;
+      float v[EPV];
+      if (e < a.dim) {
+        RowVec<T>::load(mat + (size_t)row * a.dim + e, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < EPV; ++j) v[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < EPV; ++j) {
+        const double x = (double)v[j];
+        acc = __fma_rn(x, qreg[c * EPV + j], acc);
+        if (METRIC == DRAG_METRIC_COSINE_SIM) nn = __fma_rn(x, x, nn);
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      acc += __shfl_xor_sync(FULL, acc, off);
+      if (METRIC == DRAG_METRIC_COSINE_SIM) nn += __shfl_xor_sync(FULL, nn, off);
+    }
+    float rsq = 0.f;
+    if (METRIC == DRAG_METRIC_SQEUCLIDEAN_DIST || METRIC == DRAG_METRIC_EUCLIDEAN_DIST) rsq = __ldg(a.row_sq + row);
+    const double val = metric_value<METRIC>(acc, nn, rsq, qsq, qnorm);
+    if (lane == 0) {
+      skeys[i] = key_from_double(val);
+      srows[i] = row;
+      // a NaN distance (sqrt of a negative residue, NaN input) is ordered last by the reference; the
+      // candidate filter cannot certify that case, so the caller re-runs the query through the scan
+      if (val != val) s_bad = 1;
+    }
+  }
+  int padded = 32;
+  while (padded < m) padded <<= 1;
+  for (int i = m + threadIdx.x; i < padded; i += RERANK_WARPS * 32) { skeys[i] = KEY_SENTINEL; srows[i] = 0xffffffffu; }
+  __syncthreads();
+  if (s_bad) {
+    if (threadIdx.x == 0) { a.out_status[q] = 1; a.out_count[q] = 0; }
+    return;
+  }
+  for (int size = 2; size <= padded; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (padded >> 1); t += RERANK_WARPS * 32) {
+        const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+        const int j = i + stride;
+        const bool up = (i & size) == 0;
+        const uint64_t ka = skeys[i], kb = skeys[j];
+        const uint32_t ra = srows[i], rb = srows[j];
+        const bool a_less = entry_less<uint32_t>(ka, ra, kb, rb);
+        if (up ? !a_less : a_less) { skeys[i] = kb; srows[i] = rb; skeys[j] = ka; srows[j] = ra; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < a.k; i += RERANK_WARPS * 32) {
+    const bool valid = i < want;
+    a.out_dist[(size_t)q * a.k + i] = valid ? double_from_key(skeys[i]) : __longlong_as_double(0x7ff8000000000000ll);
+    a.out_row[(size_t)q * a.k + i] = valid ? a.row_base + (long long)srows[i] : -1ll;
+  }
+  if (threadIdx.x == 0) { a.out_count[q] = want; a.out_status[q] = 0; }
+}
+
+template <typename T, int NCH>
+static int launch_rerank_m(int metric, const RerankArgs& a, int n_queries, cudaStream_t st) {
+  dim3 grid(n_queries), block(RERANK_WARPS * 32);
+  switch (metric) {
+    case DRAG_METRIC_COSINE_SIM: rerank_kernel<T, NCH, DRAG_METRIC_COSINE_SIM><<<grid, block, 0, st>>>(a); break;
+    case DRAG_METRIC_EUCLIDEAN_DIST: rerank_kernel<T, NCH, DRAG_METRIC_EUCLIDEAN_DIST><<<grid, block, 0, st>>>(a); break;
+    case DRAG_METRIC_SQEUCLIDEAN_DIST: rerank_kernel<T, NCH, DRAG_METRIC_SQEUCLIDEAN_DIST><<<grid, block, 0, st>>>(a); break;
+    default: rerank_kernel<T, NCH, DRAG_METRIC_INNER_PRODUCT><<<grid, block, 0, st>>>(a); break;
+  }
+  DRAG_CUDA_OK(cudaGetLastError());
+  return DRAG_OK;
+}
+
+template <typename T>
+static int launch_rerank(int metric, const RerankArgs& a, int n_queries, cudaStream_t st) {
+  const int chunk = 32 * RowVec<T>::EPV;
+  const int nch = (a.dim + chunk - 1) / chunk;
+  switch (nch) {
+    case 1: return launch_rerank_m<T, 1>(metric, a, n_queries, st);
+    case 2: return launch_rerank_m<T, 2>(metric, a, n_queries, st);
+    case 3: return launch_rerank_m<T, 3>(metric, a, n_queries, st);
+    case 4: return launch_rerank_m<T, 4>(metric, a, n_queries, st);
+    default: return fail(DRAG_ERR_UNSUPPORTED, "batched top-k: dim %d too large for the re-rank kernel", a.dim);
+  }
+}
+
+// workspace of the batched path
+struct BatchWorkspace {
+  double* q_sq;
+  double* q_norm;
+  __nv_bfloat16* q_bf16;
+  float* theta;
+  int* cnt;
+  int* overflow;
+  uint2* cand;
+};
+
+static int batch_cap(int k) { return k <= 128 ? 4096 : 8192; }
+
+static size_t carve_batch(int n_queries, int k, int dim, void* base, BatchWorkspace* ws) {
+  const size_t q_pad = ((size_t)n_queries + tcs::QT - 1) / tcs::QT * tcs::QT;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* ptr = base ? (void*)((unsigned char*)base + off) : nullptr;
+    off += align_up(bytes, 1024);
+    return ptr;
+  };
+  double* q_sq = (double*)take(q_pad * 8);
+  double* q_norm = (double*)take(q_pad * 8);
+  __nv_bfloat16* qb = (__nv_bfloat16*)take(q_pad * dim * 2);
+  float* theta = (float*)take(q_pad * 4);
+  int* cnt = (int*)take(q_pad * 4);
+  int* ovf = (int*)take(q_pad * 4);
+  uint2* cand = (uint2*)take(q_pad * (size_t)batch_cap(k) * 8);
+  if (ws) { ws->q_sq = q_sq; ws->q_norm = q_norm; ws->q_bf16 = qb; ws->theta = theta; ws->cnt = cnt; ws->overflow = ovf; ws->cand = cand; }
+  return off;
+}
+
+template <int MODE>
+static int launch_score(const CUtensorMap& tq, const CUtensorMap& tm, const tcs::ScoreParams& p, size_t smem, cudaStream_t st) {
+  auto kern = tcs::score_kernel<MODE>;
+  DRAG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<p.n_qtiles * p.ctas_per_qtile, tcs::THREADS, smem, st>>>(tq, tm, p);
+  DRAG_CUDA_OK(cudaGetLastError());
+  return DRAG_OK;
+}
+
 }  // namespace topk
 }  // namespace drag
 
@@ -872,4 +1063,226 @@ extern "C" int drag_rows_to_chunks(const int64_t* d_rows, int64_t n, const int64
       (long long*)d_out_doc, (long long*)d_out_chunk);
   DRAG_CUDA_OK(cudaGetLastError());
   return DRAG_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// batched tensor-core path (drag_topk_tc.cuh)
+// ---------------------------------------------------------------------------------
+extern "C" int drag_rows_to_bf16(const float* d_in, int64_t n_elems, void* d_out, void* stream) {
+  DRAG_REQUIRE(n_elems >= 0 && n_elems % 4 == 0, "drag_rows_to_bf16: element count must be a non-negative multiple of 4");
+  if (n_elems == 0) return DRAG_OK;
+  DRAG_REQUIRE(d_in && d_out, "drag_rows_to_bf16: null pointer");
+  DRAG_REQUIRE(((uintptr_t)d_in % 16) == 0 && ((uintptr_t)d_out % 8) == 0, "drag_rows_to_bf16: misaligned buffers");
+  const size_t n4 = (size_t)n_elems / 4;
+  size_t blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  tcs::rows_to_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)d_in, n4, (uint2*)d_out);
+  DRAG_CUDA_OK(cudaGetLastError());
+  return DRAG_OK;
+}
+
+extern "C" int drag_row_norm_stats(const float* d_row_sqnorm, int64_t n_rows, float* d_inv_norm, float* d_stats4, void* stream) {
+  DRAG_REQUIRE(n_rows >= 0 && d_stats4, "drag_row_norm_stats: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float init[4] = {0.f, INFINITY, 0.f, 0.f};
+  DRAG_CUDA_OK(cudaMemcpyAsync(d_stats4, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  if (n_rows == 0) return DRAG_OK;
+  DRAG_REQUIRE(d_row_sqnorm, "drag_row_norm_stats: null pointer");
+  long long blocks = (n_rows + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  tcs::row_norm_stats_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_row_sqnorm, n_rows, d_inv_norm, d_stats4);
+  DRAG_CUDA_OK(cudaGetLastError());
+  return DRAG_OK;
+}
+
+static int batch_supported(int64_t n_rows, int dim, int k, const char** why) {
+  if (dim % tcs::BK != 0 || dim > tcs::MAX_DIM) { *why = "dim must be a multiple of 64 and <= 512"; return 0; }
+  if (k > tcs::MAX_BATCH_K) { *why = "k must be <= 256"; return 0; }
+  if (n_rows >= (1ll << 31)) { *why = "n_rows must be < 2^31"; return 0; }
+  return 1;
+}
+
+extern "C" int drag_topk_batch_workspace_bytes(int device, int n_queries, int k, int dim, size_t* bytes) {
+  DRAG_REQUIRE(bytes, "drag_topk_batch_workspace_bytes: null out pointer");
+  DRAG_REQUIRE(n_queries >= 0 && k >= 1 && dim >= 1, "drag_topk_batch_workspace_bytes: bad arguments");
+  const char* why = "";
+  if (!batch_supported(0, dim, k, &why)) return fail(DRAG_ERR_UNSUPPORTED, "drag_topk_batch: %s", why);
+  (void)device;
+  *bytes = carve_batch(n_queries > 0 ? n_queries : 1, k, dim, nullptr, nullptr);
+  return DRAG_OK;
+}
+
+namespace {
+
+// query tiles per launch: the smallest number of groups whose CTA grid fills >= 95% of the SMs
+int pick_group(int n_qtiles, int sms) {
+  for (int groups = 1; groups <= n_qtiles; ++groups) {
+    const int g = (n_qtiles + groups - 1) / groups;
+    if (g > sms) continue;
+    const int used = (sms / g) * g;
+    if (used * 100 >= sms * 95 || g == 1) return g;
+  }
+  return 1;
+}
+
+__global__ void debug_keys_kernel(const uint2* cand, int cap, int n_rows, int n_queries, float* out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n_queries * n_rows) return;
+  const size_t q = i / n_rows, r = i % n_rows;
+  out[i] = __uint_as_float(cand[q * cap + r].x);
+}
+
+struct BatchPlan {
+  int mode;
+  double err_a, err_b;
+  const float* colvec;
+};
+
+}  // namespace
+
+// shared driver of drag_topk_batch and drag_debug_tc_scores
+static int run_batch(int device, const void* d_matrix, int dtype, const void* d_shadow, int64_t n_rows, int dim,
+                     const float* d_row_sqnorm, const float* d_row_inv_norm, float max_row_norm, const double* d_queries,
+                     int n_queries, int k, int metric, int64_t row_id_base, double* d_out_dist, int64_t* d_out_row,
+                     int32_t* d_out_count, int32_t* d_out_status, float* d_debug_keys, void* d_workspace,
+                     size_t workspace_bytes, cudaStream_t st) {
+  const int sms = sm_count(device);
+  if (sms <= 0) return fail(DRAG_ERR_DEVICE, "drag_topk_batch: cannot query device %d", device);
+  BatchWorkspace ws;
+  const size_t need = carve_batch(n_queries, k, dim, d_workspace, &ws);
+  DRAG_REQUIRE(workspace_bytes >= need, "drag_topk_batch: workspace too small (%zu < %zu)", workspace_bytes, need);
+  const int cap = batch_cap(k);
+  const int q_pad = (n_queries + tcs::QT - 1) / tcs::QT * tcs::QT;
+  const int n_qtiles = q_pad / tcs::QT;
+
+  // certified bound E[q] = err_a * |q| + err_b on |approximate key - exact key|:
+  //   both operands rounded to bf16 (relative 2^-9 each, Cauchy-Schwarz over the row) -> 2^-8 * 1.01,
+  //   fp32 accumulation in the tensor core -> 2^-11 allowance (measured error is ~100x smaller),
+  //   fp32 rounding of the key arithmetic (0.5*|d|^2 term / inverse norm)
+  const double c1 = ldexp(1.0, -8) * 1.01 + ldexp(1.0, -11);
+  const double dmax = (double)max_row_norm * (1.0 + 1e-6);
+  BatchPlan plan;
+  if (metric == DRAG_METRIC_INNER_PRODUCT) {
+    plan.mode = tcs::MODE_IP; plan.err_a = c1 * dmax; plan.err_b = 0.0; plan.colvec = nullptr;
+  } else if (metric == DRAG_METRIC_COSINE_SIM) {
+    plan.mode = tcs::MODE_COS; plan.err_a = c1 + ldexp(1.0, -19); plan.err_b = 0.0; plan.colvec = d_row_inv_norm;
+  } else {
+    plan.mode = tcs::MODE_L2; plan.err_a = (c1 + ldexp(1.0, -22)) * dmax; plan.err_b = ldexp(1.0, -22) * dmax * dmax;
+    plan.colvec = d_row_sqnorm;
+  }
+
+  query_prep_kernel<<<(n_queries + 63) / 64, 64, 0, st>>>(d_queries, n_queries, dim, ws.q_sq, ws.q_norm);
+  DRAG_CUDA_OK(cudaGetLastError());
+  {
+    const size_t n = (size_t)q_pad * dim;
+    tcs::queries_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_queries, n_queries, q_pad, dim, ws.q_bf16);
+    DRAG_CUDA_OK(cudaGetLastError());
+  }
+  DRAG_CUDA_OK(cudaMemsetAsync(ws.overflow, 0, (size_t)q_pad * 4, st));
+  DRAG_CUDA_OK(cudaMemsetAsync(ws.cnt, 0, (size_t)q_pad * 4, st));
+
+  CUtensorMap tq, tm;
+  int rc = make_tmap_bf16(&tq, ws.q_bf16, (uint64_t)q_pad, (uint64_t)dim, tcs::QT);
+  if (rc) return rc;
+  if ((rc = make_tmap_bf16(&tm, d_shadow, (uint64_t)n_rows, (uint64_t)dim, tcs::RT))) return rc;
+
+  const int k_blocks = dim / tcs::BK;
+  int stages = tcs::MAX_STAGES;
+  while (stages > 2 && tcs::score_smem_bytes(k_blocks, stages) > 227 * 1024) --stages;
+  const size_t smem = tcs::score_smem_bytes(k_blocks, stages);
+  DRAG_REQUIRE(smem <= 227 * 1024, "drag_topk_batch: dim %d does not fit the shared-memory plan", dim);
+  const int group = pick_group(n_qtiles, sms);
+
+  const size_t refine_smem = (size_t)cap * 8;
+  DRAG_CUDA_OK(cudaFuncSetAttribute(tcs::refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)refine_smem));
+
+  long long done = 0, bound = tcs::ROUND0_ROWS;
+  if (d_debug_keys) bound = n_rows;  // debug: one collect-all round over the whole (small) matrix
+  while (done < n_rows) {
+    const long long r1 = n_rows < bound ? n_rows : bound;
+    const long long n_tiles = (r1 - done + tcs::RT - 1) / tcs::RT;
+    for (int qt0 = 0; qt0 < n_qtiles; qt0 += group) {
+      tcs::ScoreParams p;
+      p.qt0 = qt0;
+      p.n_qtiles = (n_qtiles - qt0) < group ? (n_qtiles - qt0) : group;
+      long long per = sms / p.n_qtiles;
+      if (per > n_tiles) per = n_tiles;
+      if (per < 1) per = 1;
+      p.ctas_per_qtile = (int)per;
+      p.n_valid_q = n_queries;
+      p.row0 = done; p.row1 = r1;
+      p.k_blocks = k_blocks; p.stages = stages;
+      p.colvec = plan.colvec; p.theta = ws.theta; p.cand = ws.cand; p.cnt = ws.cnt; p.cap = cap;
+      p.collect_all = done == 0 ? 1 : 0;
+      if (plan.mode == tcs::MODE_IP) rc = launch_score<tcs::MODE_IP>(tq, tm, p, smem, st);
+      else if (plan.mode == tcs::MODE_L2) rc = launch_score<tcs::MODE_L2>(tq, tm, p, smem, st);
+      else rc = launch_score<tcs::MODE_COS>(tq, tm, p, smem, st);
+      if (rc) return rc;
+    }
+    if (d_debug_keys) {
+      // keys of round 0 sit at index == row
+      const size_t n = (size_t)n_queries * (size_t)n_rows;
+      debug_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws.cand, cap, (int)n_rows, n_queries, d_debug_keys);
+      DRAG_CUDA_OK(cudaGetLastError());
+      return DRAG_OK;
+    }
+    tcs::RefineParams rp;
+    rp.cand = ws.cand; rp.cnt = ws.cnt; rp.theta = ws.theta; rp.overflow = ws.overflow; rp.q_norm = ws.q_norm;
+    rp.err_a = plan.err_a; rp.err_b = plan.err_b; rp.cap = cap; rp.k = k;
+    rp.forced_count = done == 0 ? (int)(r1 - done) : 0;
+    tcs::refine_kernel<<<n_queries, tcs::REFINE_THREADS, refine_smem, st>>>(rp);
+    DRAG_CUDA_OK(cudaGetLastError());
+    done = r1;
+    bound *= tcs::ROUND_GROWTH;
+  }
+
+  RerankArgs a;
+  a.mat = d_matrix; a.n_rows = n_rows; a.dim = dim; a.row_sq = d_row_sqnorm; a.queries = d_queries;
+  a.q_sq = ws.q_sq; a.q_norm = ws.q_norm; a.cand = ws.cand; a.cnt = ws.cnt; a.overflow = ws.overflow;
+  a.cap = cap; a.k = k; a.row_base = row_id_base;
+  a.out_dist = d_out_dist; a.out_row = (long long*)d_out_row; a.out_count = d_out_count; a.out_status = d_out_status;
+  return dtype == DRAG_F32 ? launch_rerank<float>(metric, a, n_queries, st)
+                           : launch_rerank<__nv_bfloat16>(metric, a, n_queries, st);
+}
+
+extern "C" int drag_topk_batch(int device, const void* d_matrix, int dtype, const void* d_shadow_bf16, int64_t n_rows,
+                               int dim, const float* d_row_sqnorm, const float* d_row_inv_norm, float max_row_norm,
+                               const double* d_queries, int n_queries, int k, int metric, int64_t row_id_base,
+                               double* d_out_dist, int64_t* d_out_row, int32_t* d_out_count, int32_t* d_out_status,
+                               void* d_workspace, size_t workspace_bytes, void* stream) {
+  DRAG_REQUIRE(dtype == DRAG_F32 || dtype == DRAG_BF16, "drag_topk_batch: bad dtype %d", dtype);
+  DRAG_REQUIRE(metric >= 0 && metric <= 3, "drag_topk_batch: bad metric %d", metric);
+  DRAG_REQUIRE(k >= 1 && n_rows >= 1 && dim >= 1 && n_queries >= 0, "drag_topk_batch: bad sizes");
+  const char* why = "";
+  if (!batch_supported(n_rows, dim, k, &why)) return fail(DRAG_ERR_UNSUPPORTED, "drag_topk_batch: %s", why);
+  if (n_queries == 0) return DRAG_OK;
+  DRAG_REQUIRE(d_matrix && d_shadow_bf16 && d_queries && d_out_dist && d_out_row && d_out_count && d_out_status && d_workspace,
+               "drag_topk_batch: null pointer");
+  DRAG_REQUIRE(((uintptr_t)d_shadow_bf16 % 16) == 0 && ((uintptr_t)d_matrix % 16) == 0, "drag_topk_batch: matrix buffers must be 16-byte aligned");
+  DRAG_REQUIRE(max_row_norm >= 0.f && max_row_norm <= 1e18f, "drag_topk_batch: max_row_norm %g is not usable", (double)max_row_norm);
+  const bool needs_sq = metric == DRAG_METRIC_SQEUCLIDEAN_DIST || metric == DRAG_METRIC_EUCLIDEAN_DIST;
+  DRAG_REQUIRE(!needs_sq || d_row_sqnorm, "drag_topk_batch: (sq)euclidean metric needs d_row_sqnorm");
+  DRAG_REQUIRE(metric != DRAG_METRIC_COSINE_SIM || d_row_inv_norm, "drag_topk_batch: cosine metric needs d_row_inv_norm");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_topk_batch: cannot select device %d", device);
+  return run_batch(device, d_matrix, dtype, d_shadow_bf16, n_rows, dim, d_row_sqnorm, d_row_inv_norm, max_row_norm,
+                   d_queries, n_queries, k, metric, row_id_base, d_out_dist, d_out_row, d_out_count, d_out_status,
+                   nullptr, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int drag_debug_tc_keys(int device, const void* d_shadow_bf16, int64_t n_rows, int dim, const float* d_colvec,
+                                  int metric, const double* d_queries, int n_queries, float* d_out_keys,
+                                  void* d_workspace, size_t workspace_bytes, void* stream) {
+  DRAG_REQUIRE(d_shadow_bf16 && d_queries && d_out_keys && d_workspace, "drag_debug_tc_keys: null pointer");
+  DRAG_REQUIRE(n_rows >= 1 && n_rows <= 4096 && n_queries >= 1, "drag_debug_tc_keys: 1 <= n_rows <= 4096");
+  const char* why = "";
+  if (!batch_supported(n_rows, dim, 1, &why)) return fail(DRAG_ERR_UNSUPPORTED, "drag_debug_tc_keys: %s", why);
+  DRAG_REQUIRE(metric == DRAG_METRIC_INNER_PRODUCT || d_colvec, "drag_debug_tc_keys: this metric needs d_colvec");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_debug_tc_keys: cannot select device %d", device);
+  // k = 1 -> cap 4096 >= n_rows; the per-query key rows come back as [n_queries, n_rows]
+  const float* sq = (metric == DRAG_METRIC_SQEUCLIDEAN_DIST || metric == DRAG_METRIC_EUCLIDEAN_DIST) ? d_colvec : nullptr;
+  const float* inv = metric == DRAG_METRIC_COSINE_SIM ? d_colvec : nullptr;
+  return run_batch(device, d_shadow_bf16, DRAG_BF16, d_shadow_bf16, n_rows, dim, sq, inv, 1.0f, d_queries, n_queries, 1,
+                   metric, 0, nullptr, nullptr, nullptr, nullptr, d_out_keys, d_workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -21,6 +21,8 @@ METRIC_CODES = {
 }
 DTYPE_F32, DTYPE_BF16 = 0, 1
 MAX_K = 2048
+BATCH_MAX_K = 256      # drag_topk_batch limits (drag_topk_tc.cuh)
+BATCH_MAX_DIM = 512
 
 
 class DragError(RuntimeError):
@@ -65,6 +67,15 @@ _SIGNATURES = {
          _P, _P, _P, _P, C.c_size_t, _P],
     ),
     "drag_topk_merge": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "drag_rows_to_bf16": (C.c_int, [_P, C.c_int64, _P, _P]),
+    "drag_row_norm_stats": (C.c_int, [_P, C.c_int64, _P, _P, _P]),
+    "drag_topk_batch_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "drag_topk_batch": (
+        C.c_int,
+        [C.c_int, _P, C.c_int, _P, C.c_int64, C.c_int, _P, _P, C.c_float, _P, C.c_int, C.c_int, C.c_int, C.c_int64,
+         _P, _P, _P, _P, _P, C.c_size_t, _P],
+    ),
+    "drag_debug_tc_keys": (C.c_int, [C.c_int, _P, C.c_int64, C.c_int, _P, C.c_int, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     "drag_rows_to_chunks": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, _P, _P, _P]),
     "drag_debug_gemm": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int,
                                   C.c_float, C.c_float, _P]),

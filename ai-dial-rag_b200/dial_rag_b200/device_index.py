@@ -13,7 +13,8 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 
 from dial_rag_b200 import _native
-from dial_rag_b200._native import DTYPE_BF16, DTYPE_F32, MAX_K, METRIC_CODES, DragError
+from dial_rag_b200._native import (BATCH_MAX_DIM, BATCH_MAX_K, DTYPE_BF16, DTYPE_F32, MAX_K, METRIC_CODES,
+                                   DragError)
 
 
 def _torch():
@@ -89,6 +90,11 @@ class DeviceMatrix:
         self.n_docs = len(offs) - 1
         self.doc_offsets = torch.tensor(offs, dtype=torch.int64, device=dev)
         self._ws = {}
+        # batched tensor-core path (built lazily on the first large query batch)
+        self.batch_min_queries = 8
+        self.batch_min_rows = 8192
+        self._batch_state = None
+        self.last_batch_fallbacks = 0
 
     # ------------------------------------------------------------------ helpers
     def _check_queries(self, queries: np.ndarray) -> np.ndarray:
@@ -107,17 +113,89 @@ class DeviceMatrix:
         _native.check(self.lib.drag_topk_workspace_bytes(self.device, n_queries, k, C.byref(need)))
         return torch.empty(max(need.value, 16), dtype=torch.uint8, device=dev), need.value
 
-    # ------------------------------------------------------------------ search
-    def topk_device(self, d_queries, k: int, metric):
-        """Device in / device out: ``d_queries`` f64 ``[Q, dim]`` cuda tensor.
-
-        Returns cuda tensors ``(dist f64[Q,k], rows i64[Q,k], count i32[Q])``.
-        Asynchronous on the current stream.
-        """
+    # ------------------------------------------------------------------ batched path
+    def _batch_prepare(self):
+        """bf16 scoring copy of the rows, inverse norms and norm statistics (once per index)."""
+        if self._batch_state is not None:
+            return self._batch_state
         torch = _torch()
         dev = self.matrix.device
+        state = {"ok": False}
+        if self.dim % 64 == 0 and self.dim <= BATCH_MAX_DIM and 0 < self.n_rows < 2 ** 31:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            inv = torch.empty(self.n_rows, dtype=torch.float32, device=dev)
+            stats = torch.empty(4, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _native.check(self.lib.drag_row_norm_stats(_ptr(self.row_sq), self.n_rows, _ptr(inv), _ptr(stats), stream))
+                if self.dtype_code == DTYPE_F32:
+                    shadow = torch.empty((self.n_rows, self.dim), dtype=torch.bfloat16, device=dev)
+                    _native.check(self.lib.drag_rows_to_bf16(_ptr(self.matrix), self.n_rows * self.dim, _ptr(shadow), stream))
+                else:
+                    shadow = self.matrix
+            max_sq, min_sq, bad, _ = (float(x) for x in stats.cpu())
+            # the error certificate needs finite rows of sane magnitude (else: float64 scan only)
+            state = {
+                "ok": bad == 0 and max_sq <= 1e30,
+                "cos_ok": bad == 0 and max_sq <= 1e30 and (min_sq >= 1e-24 or min_sq == float("inf")),
+                "shadow": shadow, "inv": inv, "max_norm": float(np.sqrt(max_sq)),
+            }
+        self._batch_state = state
+        return state
+
+    def _use_batch(self, nq: int, k: int, metric_code: int) -> bool:
+        if nq < self.batch_min_queries or self.n_rows < self.batch_min_rows or k > BATCH_MAX_K:
+            return False
+        state = self._batch_prepare()
+        return bool(state["cos_ok"] if metric_code == METRIC_CODES["cosine_sim"] else state["ok"])
+
+    def _topk_batch_device(self, d_queries, k: int, metric_code: int):
+        torch = _torch()
+        dev = self.matrix.device
+        state = self._batch_state
+        nq = int(d_queries.shape[0])
+        dist = torch.empty((nq, k), dtype=torch.float64, device=dev)
+        rows = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        count = torch.empty((nq,), dtype=torch.int32, device=dev)
+        status = torch.empty((nq,), dtype=torch.int32, device=dev)
+        need = C.c_size_t(0)
+        _native.check(self.lib.drag_topk_batch_workspace_bytes(self.device, nq, k, self.dim, C.byref(need)))
+        ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _native.check(
+                self.lib.drag_topk_batch(
+                    self.device, _ptr(self.matrix), self.dtype_code, _ptr(state["shadow"]), self.n_rows, self.dim,
+                    _ptr(self.row_sq), _ptr(state["inv"]), state["max_norm"], _ptr(d_queries), nq, k, metric_code,
+                    self.row_id_base, _ptr(dist), _ptr(rows), _ptr(count), _ptr(status), _ptr(ws), need.value, stream,
+                )
+            )
+        # queries the certificate did not cover (candidate overflow, NaN distances) go through the scan
+        redo = torch.nonzero(status).flatten()
+        self.last_batch_fallbacks = int(redo.numel())
+        if redo.numel():
+            d2, r2, c2 = self._topk_scan_device(d_queries[redo].contiguous(), k, metric_code)
+            dist[redo], rows[redo], count[redo] = d2, r2, c2
+        return dist, rows, count
+
+    # ------------------------------------------------------------------ search
+    def topk_device(self, d_queries, k: int, metric, allow_batch: bool = True):
+        """Device in / device out: ``d_queries`` f64 ``[Q, dim]`` cuda tensor.
+
+        Returns cuda tensors ``(dist f64[Q,k], rows i64[Q,k], count i32[Q])``.  Small batches run
+        the float64 scan (asynchronous on the current stream); batches of ``batch_min_queries`` or
+        more run the tensor-core candidate pass + float64 re-rank (same results; synchronises once
+        to read the per-query status).
+        """
         if not 1 <= k <= MAX_K:
             raise DragError(3, f"k={k} outside the supported range 1..{MAX_K}")
+        code = _metric_code(metric)
+        if allow_batch and self._use_batch(int(d_queries.shape[0]), k, code):
+            return self._topk_batch_device(d_queries, k, code)
+        return self._topk_scan_device(d_queries, k, code)
+
+    def _topk_scan_device(self, d_queries, k: int, metric_code: int):
+        torch = _torch()
+        dev = self.matrix.device
         nq = int(d_queries.shape[0])
         dist = torch.empty((nq, k), dtype=torch.float64, device=dev)
         rows = torch.empty((nq, k), dtype=torch.int64, device=dev)
@@ -128,7 +206,7 @@ class DeviceMatrix:
             _native.check(
                 self.lib.drag_topk(
                     self.device, _ptr(self.matrix), self.dtype_code, self.n_rows, self.dim,
-                    _ptr(self.row_sq), _ptr(d_queries), nq, k, _metric_code(metric), self.row_id_base,
+                    _ptr(self.row_sq), _ptr(d_queries), nq, k, metric_code, self.row_id_base,
                     _ptr(dist), _ptr(rows), _ptr(count), _ptr(ws), ws_bytes, stream,
                 )
             )

@@ -188,6 +188,43 @@ int drag_rows_to_chunks(const int64_t* d_rows, int64_t n, const int64_t* d_doc_o
                         int n_docs, const int64_t* d_row_chunk_ids, int64_t* d_out_doc,
                         int64_t* d_out_chunk, void* stream);
 
+
+/* ------------------------------------------------------------------------- *
+ *  Batched exact top-k (tensor cores + float64 re-rank)                      *
+ *  same contract as drag_topk -- the reference's per-query find()            *
+ *  (embeddings_index.py:62-89) for MANY queries sharing one pass over the    *
+ *  matrix (langchain's retriever.batch / eval/eval_retriever.py:97).         *
+ * ------------------------------------------------------------------------- */
+
+/* bf16 (round-to-nearest-even) copy of a float32 matrix: the tensor-core scoring operand. */
+int drag_rows_to_bf16(const float* d_in, int64_t n_elems, void* d_out, void* stream);
+
+/*
+ * d_stats4 <- {max |row|^2, min non-zero |row|^2, number of non-finite |row|^2, 0};
+ * d_inv_norm (optional) <- 1 / max(|row|, 1e-8)   (cosine keys).  Input: drag_row_sqnorm output.
+ */
+int drag_row_norm_stats(const float* d_row_sqnorm, int64_t n_rows, float* d_inv_norm, float* d_stats4, void* stream);
+
+int drag_topk_batch_workspace_bytes(int device, int n_queries, int k, int dim, size_t* bytes);
+
+/*
+ * Exact top-k of a batch of queries: candidates are generated with bf16 tcgen05 scores under a
+ * certified error bound, survivors are re-scored in float64 exactly like drag_topk and sorted on
+ * (distance, row id).  Results are identical to drag_topk's.
+ *   d_matrix       the matrix the exact scores are taken from (f32 or bf16)
+ *   d_shadow_bf16  bf16 copy of it (== d_matrix when dtype is bf16), 16-byte aligned
+ *   d_row_inv_norm from drag_row_norm_stats (cosine only, else may be NULL)
+ *   max_row_norm   sqrt(stats[0])
+ *   d_out_status   i32[n_queries]: 0 = answered; 1 = the certificate did not cover this query
+ *                  (candidate overflow, NaN distances) -> the caller re-runs it through drag_topk.
+ * Requires dim % 64 == 0, dim <= 512, k <= 256, finite rows.  Asynchronous on `stream`.
+ */
+int drag_topk_batch(int device, const void* d_matrix, int dtype, const void* d_shadow_bf16, int64_t n_rows,
+                    int dim, const float* d_row_sqnorm, const float* d_row_inv_norm, float max_row_norm,
+                    const double* d_queries, int n_queries, int k, int metric, int64_t row_id_base,
+                    double* d_out_dist, int64_t* d_out_row, int32_t* d_out_count, int32_t* d_out_status,
+                    void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------- *
  *  Kernel-level entry points (parity tests only): run ONE fused kernel.      *
  * ------------------------------------------------------------------------- */
@@ -208,6 +245,16 @@ int drag_debug_gemm(int device, int variant, const void* d_a, const void* d_w, c
 /* ctx[T, heads*32] = softmax(Q K^T / sqrt(32)) V per packed sequence; d_qkv is bf16 [T, 3*heads*32]. */
 int drag_debug_attention(int device, const void* d_qkv, void* d_ctx, const int32_t* d_cu_seqlens,
                          int n_seq, int max_len, int heads, void* stream);
+
+/*
+ * Approximate "bigger is better" keys of the batched path's score kernel for every (query, row):
+ * inner product: s; (sq)euclidean: s - |d|^2/2 (d_colvec = row_sqnorm); cosine: s / |d| (d_colvec =
+ * inverse norms), with s = bf16(q) . bf16(d) accumulated in fp32 by tcgen05.  n_rows <= 4096.
+ * d_out_keys: f32[n_queries, n_rows].  Workspace: drag_topk_batch_workspace_bytes(.., k = 1, ..).
+ */
+int drag_debug_tc_keys(int device, const void* d_shadow_bf16, int64_t n_rows, int dim, const float* d_colvec,
+                       int metric, const double* d_queries, int n_queries, float* d_out_keys,
+                       void* d_workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }
