@@ -745,7 +745,7 @@ struct RerankArgs {
   const double* queries;
   const double* q_sq;
   const double* q_norm;
-  const uint2* cand;
+  const uint2* cand;   // [Qpad][SURV_CAP] survivors of the last refine
   const int* cnt;
   const int* overflow;
   int cap, k;
@@ -885,12 +885,13 @@ struct BatchWorkspace {
   double* q_norm;
   __nv_bfloat16* q_bf16;
   float* theta;
-  int* cnt;
+  int* cnt;        // [Qpad][MAX_SLOTS]
+  int2* meta;      // [Qpad]
+  int* surv_cnt;   // [Qpad]
   int* overflow;
-  uint2* cand;
+  uint2* pool;     // [Qpad][POOL_CAP]
+  uint2* surv;     // [Qpad][SURV_CAP]
 };
-
-static int batch_cap(int k) { return k <= 128 ? 4096 : 8192; }
 
 static size_t carve_batch(int n_queries, int k, int dim, void* base, BatchWorkspace* ws) {
   const size_t q_pad = ((size_t)n_queries + tcs::QT - 1) / tcs::QT * tcs::QT;
@@ -904,10 +905,17 @@ static size_t carve_batch(int n_queries, int k, int dim, void* base, BatchWorksp
   double* q_norm = (double*)take(q_pad * 8);
   __nv_bfloat16* qb = (__nv_bfloat16*)take(q_pad * dim * 2);
   float* theta = (float*)take(q_pad * 4);
-  int* cnt = (int*)take(q_pad * 4);
+  int* cnt = (int*)take(q_pad * (size_t)tcs::MAX_SLOTS * 4);
+  int2* meta = (int2*)take(q_pad * 8);
+  int* scnt = (int*)take(q_pad * 4);
   int* ovf = (int*)take(q_pad * 4);
-  uint2* cand = (uint2*)take(q_pad * (size_t)batch_cap(k) * 8);
-  if (ws) { ws->q_sq = q_sq; ws->q_norm = q_norm; ws->q_bf16 = qb; ws->theta = theta; ws->cnt = cnt; ws->overflow = ovf; ws->cand = cand; }
+  uint2* pool = (uint2*)take(q_pad * (size_t)tcs::POOL_CAP * 8);
+  uint2* surv = (uint2*)take(q_pad * (size_t)tcs::SURV_CAP * 8);
+  (void)k;
+  if (ws) {
+    ws->q_sq = q_sq; ws->q_norm = q_norm; ws->q_bf16 = qb; ws->theta = theta; ws->cnt = cnt; ws->meta = meta;
+    ws->surv_cnt = scnt; ws->overflow = ovf; ws->pool = pool; ws->surv = surv;
+  }
   return off;
 }
 
@@ -1125,11 +1133,17 @@ int pick_group(int n_qtiles, int sms) {
   return 1;
 }
 
-__global__ void debug_keys_kernel(const uint2* cand, int cap, int n_rows, int n_queries, float* out) {
+// collect-all round: every region entry carries (key, row); scatter the keys to out[q][row]
+__global__ void debug_keys_kernel(const uint2* pool, const int* cnt, const int2* meta, int n_rows, int n_queries, float* out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)n_queries * n_rows) return;
-  const size_t q = i / n_rows, r = i % n_rows;
-  out[i] = __uint_as_float(cand[q * cap + r].x);
+  if (i >= (size_t)n_queries * tcs::POOL_CAP) return;
+  const size_t q = i / tcs::POOL_CAP;
+  const int e = (int)(i % tcs::POOL_CAP);
+  const int2 m = meta[q];
+  const int slot = e / m.y, j = e % m.y;
+  if (slot >= m.x || j >= cnt[q * tcs::MAX_SLOTS + slot]) return;
+  const uint2 v = pool[i];
+  if ((int)v.y < n_rows) out[q * n_rows + v.y] = __uint_as_float(v.x);
 }
 
 struct BatchPlan {
@@ -1151,7 +1165,6 @@ static int run_batch(int device, const void* d_matrix, int dtype, const void* d_
   BatchWorkspace ws;
   const size_t need = carve_batch(n_queries, k, dim, d_workspace, &ws);
   DRAG_REQUIRE(workspace_bytes >= need, "drag_topk_batch: workspace too small (%zu < %zu)", workspace_bytes, need);
-  const int cap = batch_cap(k);
   const int q_pad = (n_queries + tcs::QT - 1) / tcs::QT * tcs::QT;
   const int n_qtiles = q_pad / tcs::QT;
 
@@ -1179,7 +1192,7 @@ static int run_batch(int device, const void* d_matrix, int dtype, const void* d_
     DRAG_CUDA_OK(cudaGetLastError());
   }
   DRAG_CUDA_OK(cudaMemsetAsync(ws.overflow, 0, (size_t)q_pad * 4, st));
-  DRAG_CUDA_OK(cudaMemsetAsync(ws.cnt, 0, (size_t)q_pad * 4, st));
+  DRAG_CUDA_OK(cudaMemsetAsync(ws.surv_cnt, 0, (size_t)q_pad * 4, st));
 
   CUtensorMap tq, tm;
   int rc = make_tmap_bf16(&tq, ws.q_bf16, (uint64_t)q_pad, (uint64_t)dim, tcs::QT);
@@ -1193,7 +1206,7 @@ static int run_batch(int device, const void* d_matrix, int dtype, const void* d_
   DRAG_REQUIRE(smem <= 227 * 1024, "drag_topk_batch: dim %d does not fit the shared-memory plan", dim);
   const int group = pick_group(n_qtiles, sms);
 
-  const size_t refine_smem = (size_t)cap * 8;
+  const size_t refine_smem = tcs::refine_smem_bytes();
   DRAG_CUDA_OK(cudaFuncSetAttribute(tcs::refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)refine_smem));
 
   long long done = 0, bound = tcs::ROUND0_ROWS;
@@ -1212,7 +1225,8 @@ static int run_batch(int device, const void* d_matrix, int dtype, const void* d_
       p.n_valid_q = n_queries;
       p.row0 = done; p.row1 = r1;
       p.k_blocks = k_blocks; p.stages = stages;
-      p.colvec = plan.colvec; p.theta = ws.theta; p.cand = ws.cand; p.cnt = ws.cnt; p.cap = cap;
+      p.colvec = plan.colvec; p.theta = ws.theta; p.pool = ws.pool; p.cnt = ws.cnt; p.meta = ws.meta;
+      p.region_cap = tcs::POOL_CAP / p.ctas_per_qtile;
       p.collect_all = done == 0 ? 1 : 0;
       if (plan.mode == tcs::MODE_IP) rc = launch_score<tcs::MODE_IP>(tq, tm, p, smem, st);
       else if (plan.mode == tcs::MODE_L2) rc = launch_score<tcs::MODE_L2>(tq, tm, p, smem, st);
@@ -1221,15 +1235,15 @@ static int run_batch(int device, const void* d_matrix, int dtype, const void* d_
     }
     if (d_debug_keys) {
       // keys of round 0 sit at index == row
-      const size_t n = (size_t)n_queries * (size_t)n_rows;
-      debug_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws.cand, cap, (int)n_rows, n_queries, d_debug_keys);
+      const size_t n = (size_t)n_queries * (size_t)tcs::POOL_CAP;
+      debug_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws.pool, ws.cnt, ws.meta, (int)n_rows, n_queries, d_debug_keys);
       DRAG_CUDA_OK(cudaGetLastError());
       return DRAG_OK;
     }
     tcs::RefineParams rp;
-    rp.cand = ws.cand; rp.cnt = ws.cnt; rp.theta = ws.theta; rp.overflow = ws.overflow; rp.q_norm = ws.q_norm;
-    rp.err_a = plan.err_a; rp.err_b = plan.err_b; rp.cap = cap; rp.k = k;
-    rp.forced_count = done == 0 ? (int)(r1 - done) : 0;
+    rp.pool = ws.pool; rp.cnt = ws.cnt; rp.meta = ws.meta; rp.surv = ws.surv; rp.surv_cnt = ws.surv_cnt;
+    rp.theta = ws.theta; rp.overflow = ws.overflow; rp.q_norm = ws.q_norm;
+    rp.err_a = plan.err_a; rp.err_b = plan.err_b; rp.k = k;
     tcs::refine_kernel<<<n_queries, tcs::REFINE_THREADS, refine_smem, st>>>(rp);
     DRAG_CUDA_OK(cudaGetLastError());
     done = r1;
@@ -1238,8 +1252,8 @@ static int run_batch(int device, const void* d_matrix, int dtype, const void* d_
 
   RerankArgs a;
   a.mat = d_matrix; a.n_rows = n_rows; a.dim = dim; a.row_sq = d_row_sqnorm; a.queries = d_queries;
-  a.q_sq = ws.q_sq; a.q_norm = ws.q_norm; a.cand = ws.cand; a.cnt = ws.cnt; a.overflow = ws.overflow;
-  a.cap = cap; a.k = k; a.row_base = row_id_base;
+  a.q_sq = ws.q_sq; a.q_norm = ws.q_norm; a.cand = ws.surv; a.cnt = ws.surv_cnt; a.overflow = ws.overflow;
+  a.cap = tcs::SURV_CAP; a.k = k; a.row_base = row_id_base;
   a.out_dist = d_out_dist; a.out_row = (long long*)d_out_row; a.out_count = d_out_count; a.out_status = d_out_status;
   return dtype == DRAG_F32 ? launch_rerank<float>(metric, a, n_queries, st)
                            : launch_rerank<__nv_bfloat16>(metric, a, n_queries, st);
@@ -1280,7 +1294,7 @@ extern "C" int drag_debug_tc_keys(int device, const void* d_shadow_bf16, int64_t
   DRAG_REQUIRE(metric == DRAG_METRIC_INNER_PRODUCT || d_colvec, "drag_debug_tc_keys: this metric needs d_colvec");
   DeviceGuard guard(device);
   if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_debug_tc_keys: cannot select device %d", device);
-  // k = 1 -> cap 4096 >= n_rows; the per-query key rows come back as [n_queries, n_rows]
+  // one collect-all round over the whole matrix; the keys come back as [n_queries, n_rows]
   const float* sq = (metric == DRAG_METRIC_SQEUCLIDEAN_DIST || metric == DRAG_METRIC_EUCLIDEAN_DIST) ? d_colvec : nullptr;
   const float* inv = metric == DRAG_METRIC_COSINE_SIM ? d_colvec : nullptr;
   return run_batch(device, d_shadow_bf16, DRAG_BF16, d_shadow_bf16, n_rows, dim, sq, inv, 1.0f, d_queries, n_queries, 1,

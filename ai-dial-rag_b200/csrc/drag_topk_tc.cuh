@@ -44,6 +44,9 @@ constexpr int MAX_BATCH_K = 256;
 constexpr int RERANK_MAX = 2048;             // candidates the re-rank kernel sorts per query
 constexpr int ROUND0_ROWS = 2048;            // first round collects every score of these rows
 constexpr int ROUND_GROWTH = 8;
+constexpr int POOL_CAP = 8192;               // new candidates per query and round (all regions together)
+constexpr int SURV_CAP = RERANK_MAX;         // candidates kept per query between rounds
+constexpr int MAX_SLOTS = 160;               // >= CTAs per query tile (<= number of SMs)
 
 enum { MODE_IP = 0, MODE_L2 = 1, MODE_COS = 2 };
 
@@ -57,10 +60,11 @@ struct ScoreParams {
   int stages;
   const float* colvec;   // MODE_L2: |d|^2 (float32, numpy order)  MODE_COS: 1 / max(|d|, 1e-8)
   const float* theta;    // [Qpad]
-  uint2* cand;           // [Qpad][cap]  (key bits, row)
-  int* cnt;              // [Qpad]
-  int cap;
-  int collect_all;       // round 0: every score is stored at index (row - row0)
+  uint2* pool;           // [Qpad][POOL_CAP] (key bits, row): region `slot` of a query belongs to ONE CTA
+  int* cnt;              // [Qpad][MAX_SLOTS] entries pushed into each region by this launch
+  int2* meta;            // [Qpad] (regions used, region capacity) of this launch
+  int region_cap;        // POOL_CAP / ctas_per_qtile
+  int collect_all;       // round 0: every score is a candidate
 };
 
 __host__ __device__ inline size_t score_smem_bytes(int k_blocks, int stages) {
@@ -170,7 +174,9 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     const bool all = p.collect_all != 0;
     float theta = INFINITY;
     if (q_ok) theta = all ? -INFINITY : __ldg(p.theta + q);
-    uint2* my_cand = p.cand + (size_t)q * p.cap;
+    // candidates go to a region only this thread writes: no atomics, stores never stall the warp
+    uint2* region = p.pool + ((size_t)q * POOL_CAP + (size_t)slot * p.region_cap);
+    int n_mine = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = slot; t < n_tiles; t += p.ctas_per_qtile) {
@@ -211,14 +217,22 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
           mx = fmaxf(mx, key[i]);
         }
         if ((all && q_ok) || mx >= theta) {
-          // rare path (a handful of rows per query and round once the threshold is tight)
+          // Rare once the threshold is tight (a handful of rows per query and round).  Branch-free:
+          // a predicated 8-byte store per column, so a warp whose lanes hit in different columns
+          // does not pay 32 divergent branches.
+          const int room = p.region_cap;
+          const uint32_t row_c0 = (uint32_t)(tile_row0 + c0);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            if ((all || key[i] >= theta) && c0 + i < n_valid) {
-              const uint32_t row = (uint32_t)(tile_row0 + c0 + i);
-              const int idx = all ? (int)(tile_row0 - p.row0) + c0 + i : atomicAdd(p.cnt + q, 1);
-              if (idx < p.cap) my_cand[idx] = make_uint2(__float_as_uint(key[i]), row);
-            }
+            const bool hit = (all || key[i] >= theta) && (c0 + i < n_valid);
+            const uint32_t do_store = (hit && n_mine < room) ? 1u : 0u;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.ne.b32 p, %0, 0;\n\t"
+                "@p st.global.v2.b32 [%1], {%2, %3};\n\t}"
+                ::"r"(do_store), "l"(region + n_mine), "r"(__float_as_uint(key[i])), "r"(row_c0 + (uint32_t)i)
+                : "memory");
+            n_mine += hit ? 1 : 0;
           }
         }
       }
@@ -226,6 +240,10 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (q_ok) {
+      p.cnt[(size_t)q * MAX_SLOTS + slot] = n_mine;  // > region_cap means the region overflowed
+      if (slot == 0) p.meta[q] = make_int2(p.ctas_per_qtile, p.region_cap);
     }
   }
 
@@ -291,14 +309,16 @@ __global__ void row_norm_stats_kernel(const float* __restrict__ sq, long long n,
 // refine: new threshold + compaction, one CTA per query
 // ---------------------------------------------------------------------------------
 struct RefineParams {
-  uint2* cand;
-  int* cnt;
+  const uint2* pool;      // new candidates of the round that just ran
+  const int* cnt;
+  const int2* meta;
+  uint2* surv;            // [Qpad][SURV_CAP] candidates kept from earlier rounds
+  int* surv_cnt;          // [Qpad]
   float* theta;
   int* overflow;
   const double* q_norm;   // max(|q|, 1e-8)
   double err_a, err_b;    // E[q] = err_a * |q| + err_b
-  int cap, k;
-  int forced_count;       // > 0: round 0, every query has exactly this many entries
+  int k;
 };
 
 __device__ __forceinline__ uint32_t ordered_from_float_bits(uint32_t b) {
@@ -311,28 +331,61 @@ __device__ __forceinline__ float float_from_ordered(uint32_t o) {
 }
 
 constexpr int REFINE_THREADS = 256;
+constexpr int REFINE_MAX = POOL_CAP + SURV_CAP;   // entries a refine CTA can hold in shared memory
+
+__host__ __device__ inline size_t refine_smem_bytes() { return (size_t)REFINE_MAX * 8; }
 
 __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams p) {
   extern __shared__ __align__(16) unsigned char smem_refine[];
-  uint32_t* keys = reinterpret_cast<uint32_t*>(smem_refine);  // [cap] ordered keys
-  uint32_t* rows = keys + p.cap;                                // [cap]
+  uint32_t* keys = reinterpret_cast<uint32_t*>(smem_refine);  // [REFINE_MAX] ordered keys
+  uint32_t* rows = keys + REFINE_MAX;                           // [REFINE_MAX]
   __shared__ uint32_t hist[256];
+  __shared__ int offs[MAX_SLOTS + 1];
   __shared__ uint32_t s_prefix, s_remaining, s_out;
+  __shared__ int s_fail;
   const int q = blockIdx.x;
   const int tid = threadIdx.x;
   if (p.overflow[q]) return;
-  const int n = p.forced_count > 0 ? p.forced_count : p.cnt[q];
-  if (n > p.cap) {
-    if (tid == 0) { p.overflow[q] = 1; p.theta[q] = INFINITY; p.cnt[q] = 0; }
+  const int2 meta = p.meta[q];
+  const int n_slots = meta.x, region_cap = meta.y;
+  const int n_old = p.surv_cnt[q];
+  if (tid == 0) {
+    int total = 0, fail = 0;
+    for (int s = 0; s < n_slots; ++s) {
+      const int c = p.cnt[(size_t)q * MAX_SLOTS + s];
+      if (c > region_cap) fail = 1;
+      offs[s] = total;
+      total += c;
+    }
+    offs[n_slots] = total;
+    if (n_old + total > REFINE_MAX) fail = 1;
+    s_fail = fail;
+    s_prefix = 0; s_remaining = (uint32_t)p.k; s_out = 0;
+  }
+  __syncthreads();
+  if (s_fail) {
+    if (tid == 0) { p.overflow[q] = 1; p.theta[q] = INFINITY; p.surv_cnt[q] = 0; }
     return;
   }
-  uint2* mine = p.cand + (size_t)q * p.cap;
-  for (int i = tid; i < n; i += REFINE_THREADS) {
+  const int n_new = offs[n_slots];
+  const int n = n_old + n_new;
+  uint2* mine = p.surv + (size_t)q * SURV_CAP;
+  for (int i = tid; i < n_old; i += REFINE_THREADS) {
     const uint2 e = mine[i];
     keys[i] = ordered_from_float_bits(e.x);
     rows[i] = e.y;
   }
-  if (tid == 0) { s_prefix = 0; s_remaining = (uint32_t)p.k; s_out = 0; }
+  const uint2* pool = p.pool + (size_t)q * POOL_CAP;
+  for (int j = tid; j < n_new; j += REFINE_THREADS) {
+    int lo = 0, hi = n_slots;  // last slot with offs[slot] <= j
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (offs[mid] <= j) lo = mid; else hi = mid;
+    }
+    const uint2 e = pool[(size_t)lo * region_cap + (j - offs[lo])];
+    keys[n_old + j] = ordered_from_float_bits(e.x);
+    rows[n_old + j] = e.y;
+  }
   __syncthreads();
   float theta_new = -INFINITY;
   if (n >= p.k) {
@@ -347,15 +400,30 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams p) 
         if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 255u], 1u);
       }
       __syncthreads();
-      if (tid == 0) {
-        uint32_t remaining = s_remaining;
-        int b = 255;
-        for (; b > 0; --b) {
-          if (hist[b] >= remaining) break;
-          remaining -= hist[b];
+      if (tid < 32) {
+        // find the bin where the count from the top reaches `remaining`: lane l owns bins [8l, 8l+8)
+        uint32_t mine8[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { mine8[j] = hist[tid * 8 + j]; sum += mine8[j]; }
+        uint32_t above = sum;  // inclusive suffix sum over lanes (lane 31 = top bins)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t v = __shfl_down_sync(0xffffffffu, above, o);
+          if (tid + o < 32) above += v;
         }
-        s_prefix = prefix | ((uint32_t)b << shift);
-        s_remaining = remaining;
+        const uint32_t remaining = s_remaining;
+        const unsigned reach = __ballot_sync(0xffffffffu, above >= remaining);
+        const int owner = reach ? 31 - __clz(reach) : 0;   // highest lane whose suffix reaches it
+        if (tid == owner) {
+          uint32_t left = remaining - (above - sum);         // still to find inside this lane's bins
+          int b = 7;
+          for (; b > 0; --b) {
+            if (mine8[b] >= left) break;
+            left -= mine8[b];
+          }
+          s_prefix = prefix | ((uint32_t)(tid * 8 + b) << shift);
+          s_remaining = left;
+        }
       }
       __syncthreads();
     }
@@ -364,7 +432,7 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams p) 
     theta_new = __double2float_rd((double)kth - margin);
     if (!(theta_new == theta_new)) theta_new = -INFINITY;
   }
-  // compaction (order is irrelevant: the re-rank sorts on exact scores)
+  // survivors (order is irrelevant: the re-rank sorts on exact scores)
   const uint32_t theta_ord = ordered_from_float_bits(__float_as_uint(theta_new));
   for (int i0 = 0; i0 < n; i0 += REFINE_THREADS) {
     const int i = i0 + tid;
@@ -375,11 +443,14 @@ __global__ void __launch_bounds__(REFINE_THREADS) refine_kernel(RefineParams p) 
     base = __shfl_sync(0xffffffffu, base, 0);
     if (keep) {
       const uint32_t pos = base + __popc(ballot & ((1u << (tid & 31)) - 1u));
-      mine[pos] = make_uint2(__float_as_uint(float_from_ordered(keys[i])), rows[i]);
+      if (pos < (uint32_t)SURV_CAP) mine[pos] = make_uint2(__float_as_uint(float_from_ordered(keys[i])), rows[i]);
     }
   }
   __syncthreads();
-  if (tid == 0) { p.cnt[q] = (int)s_out; p.theta[q] = theta_new; }
+  if (tid == 0) {
+    if (s_out > (uint32_t)SURV_CAP) { p.overflow[q] = 1; p.theta[q] = INFINITY; p.surv_cnt[q] = 0; }
+    else { p.surv_cnt[q] = (int)s_out; p.theta[q] = theta_new; }
+  }
 }
 
 }  // namespace tcs
