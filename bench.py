@@ -195,6 +195,35 @@ def run_reference(args, rank: int):
 # ------------------------------------------------------------------------------------------
 # secondary metric: exact top-k search (single GPU legs)
 # ------------------------------------------------------------------------------------------
+def search_roofline(peaks, n_queries: int, rows: int, ms: float, elem_bytes: int, batched: bool):
+    """(roofline dict, path description, matrix passes) of one search batch on one GPU."""
+    if batched:
+        # tensor-core candidate pass + float64 re-rank: one read of the bf16 scoring copy per group of
+        # query tiles; bound = max(bytes / HBM peak, 2*Q*N*D flop / bf16 peak)
+        n_qt, sms = -(-n_queries // 128), 148
+        groups = next(g for g in range(1, n_qt + 1)   # mirrors pick_group() in drag_topk.cu
+                      if (sms // -(-n_qt // g)) * -(-n_qt // g) * 100 >= sms * 95 or -(-n_qt // g) == 1)
+        flops = 2.0 * n_queries * rows * HIDDEN
+        t_mma = flops / (peaks["tflops_burst"] * 1e12)
+        t_hbm = rows * HIDDEN * 2 / (peaks["hbm_gbs"] * 1e9)
+        bound = "tensor" if t_mma >= t_hbm else "hbm"
+        roof = {"bound": bound,
+                "achieved": flops / (ms / 1e3) / 1e12 if bound == "tensor" else rows * HIDDEN * 2 / (ms / 1e3) / 1e9,
+                "peak": peaks["tflops_burst"] if bound == "tensor" else peaks["hbm_gbs"],
+                "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                "frac": max(t_mma, t_hbm) / (ms / 1e3),
+                "t_hbm_ms": t_hbm * 1e3, "t_mma_ms": t_mma * 1e3,
+                "note": "algorithmic work = ONE pass over the matrix per query batch: 2*Q*N*D flop on the bf16 scoring "
+                        "copy (N*D*2 bytes); the binding one of the two is reported; peak = measured bf16 burst / HBM copy"}
+        return roof, "tcgen05 bf16 candidate scores under a certified error bound + float64 re-rank (drag_topk_batch)", groups
+    passes = -(-n_queries // 4) if n_queries >= 4 else 1
+    bytes_per_pass = rows * HIDDEN * elem_bytes
+    roof = {"bound": "hbm", "achieved": passes * bytes_per_pass / (ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"],
+            "unit": "GB/s", "frac": passes * bytes_per_pass / (ms / 1e3) / 1e9 / peaks["hbm_gbs"],
+            "note": "algorithmic bytes = one read of the matrix per pass of <=4 queries"}
+    return roof, "float64 scan (drag_topk)", passes
+
+
 def bench_search(torch, device, peaks, rows: int, n_queries: int, k: int, steps: int, warmup: int, seed: int):
     from dial_rag_b200.device_index import DeviceMatrix
 
@@ -224,32 +253,7 @@ def bench_search(torch, device, peaks, rows: int, n_queries: int, k: int, steps:
         dm.topk(q_host, k, "inner_product")
     e2e_ms = 1e3 * (time.perf_counter() - t0) / steps
     batched = dm._use_batch(n_queries, k, 3)
-    if batched:
-        # tensor-core candidate pass + float64 re-rank: one read of the bf16 scoring copy per group of
-        # query tiles; SURVEY 8d: bound = max(bytes / HBM peak, 2*Q*N*D flop / bf16 peak)
-        n_qt, sms = -(-n_queries // 128), 148
-        groups = next(g for g in range(1, n_qt + 1)   # mirrors pick_group() in drag_topk.cu
-                      if (sms // -(-n_qt // g)) * -(-n_qt // g) * 100 >= sms * 95 or -(-n_qt // g) == 1)
-        flops = 2.0 * n_queries * rows * HIDDEN
-        t_mma = flops / (peaks["tflops_burst"] * 1e12)
-        t_hbm = rows * HIDDEN * 2 / (peaks["hbm_gbs"] * 1e9)
-        bound = "tensor" if t_mma >= t_hbm else "hbm"
-        roof = {"bound": bound, "achieved": flops / (ms / 1e3) / 1e12 if bound == "tensor" else rows * HIDDEN * 2 / (ms / 1e3) / 1e9,
-                "peak": peaks["tflops_burst"] if bound == "tensor" else peaks["hbm_gbs"],
-                "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
-                "frac": max(t_mma, t_hbm) / (ms / 1e3),
-                "t_hbm_ms": t_hbm * 1e3, "t_mma_ms": t_mma * 1e3,
-                "note": "algorithmic work = ONE pass over the matrix per query batch: 2*Q*N*D flop on the bf16 scoring copy "
-                        "(N*D*2 bytes); the binding one of the two is reported; peak = measured bf16 burst / HBM copy"}
-        path = "tcgen05 bf16 candidate scores under a certified error bound + float64 re-rank (drag_topk_batch)"
-        passes = groups
-    else:
-        passes = -(-n_queries // 4) if n_queries >= 4 else 1
-        bytes_per_pass = rows * HIDDEN * 4
-        roof = {"bound": "hbm", "achieved": passes * bytes_per_pass / (ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": passes * bytes_per_pass / (ms / 1e3) / 1e9 / peaks["hbm_gbs"],
-                "note": "algorithmic bytes = one read of the matrix per pass of <=4 queries"}
-        path = "float64 scan (drag_topk)"
+    roof, path, passes = search_roofline(peaks, n_queries, rows, ms, 4, batched)
     out = {
         "workload": f"exact top-{k} inner product, {rows}x{HIDDEN} fp32 index resident in HBM, batch {n_queries} queries; {path}",
         "queries_per_s": n_queries / (ms / 1e3), "ms_per_batch": ms,
@@ -290,15 +294,16 @@ def bench_search_sharded(torch, dist, device, rank, world, peaks, rows_per_gpu: 
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     sec = float(dt[0]) / steps
-    passes = -(-n_queries // 4)
-    bytes_per_pass = rows_per_gpu * HIDDEN * 2
+    roof, path, passes = search_roofline(peaks, n_queries, rows_per_gpu, sec * 1e3, 2,
+                                         idx._matrix._use_batch(n_queries, k, 3))
+    roof["unit"] += " per GPU"
     return {
         "workload": f"exact top-{k} inner product, {world * rows_per_gpu}x{HIDDEN} bf16 index row-sharded over {world} GPUs, "
-                    f"batch {n_queries} replicated queries, NCCL all-gather candidate merge (host queries in, host results out)",
+                    f"batch {n_queries} replicated queries, NCCL all-gather candidate merge (host queries in, host results out); {path}",
         "queries_per_s": n_queries / sec, "ms_per_batch": sec * 1e3,
         "allgather_bytes_per_rank": n_queries * (2 * k + 1) * 8,
-        "roofline": {"bound": "hbm", "achieved": passes * bytes_per_pass / sec / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s per GPU",
-                     "frac": passes * bytes_per_pass / sec / 1e9 / peaks["hbm_gbs"]},
+        "matrix_passes_per_batch": passes,
+        "roofline": roof,
         "first_result_row": int(out[1][0, 0]),
     }
 
@@ -333,7 +338,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--search-rows", type=int, default=10_000_000)
     ap.add_argument("--shard-rows", type=int, default=12_500_000, help="rows per GPU of the sharded bf16 index (N>1)")
-    ap.add_argument("--shard-queries", type=int, default=256)
+    ap.add_argument("--shard-queries", type=int, default=4096)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -472,7 +477,8 @@ def main() -> None:
 
     if world == 1 and not args.no_search:
         try:
-            search = {"batch": bench_search(torch, device, peaks, args.search_rows, 1000, 100, steps=2, warmup=1, seed=2),
+            search = {"batch": bench_search(torch, device, peaks, args.search_rows, 1000, 100, steps=5, warmup=2, seed=2),
+                      "batch256_top20_1m": bench_search(torch, device, peaks, 1_000_000, 256, 20, steps=20, warmup=3, seed=5),
                       "single_query": bench_search(torch, device, peaks, 1_000_000, 1, 20, steps=50, warmup=5, seed=5)}
             if not args.no_cpu_baseline:
                 search["cpu_baseline"] = cpu_search_baseline()
