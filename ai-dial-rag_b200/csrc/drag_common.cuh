@@ -47,6 +47,8 @@ int sm_count(int device);
 // (out-of-bounds rows/columns read as zero and are clipped on stores).  The driver entry point
 // cuTensorMapEncodeTiled is resolved at run time, so libcuda is not a link-time dependency.
 int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+// same with a box of box_cols (16, 32 or 64) columns: the swizzle span equals the box row (32/64/128 bytes)
+int make_tmap_bf16_box(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols);
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 

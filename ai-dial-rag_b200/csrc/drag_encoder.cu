@@ -11,11 +11,14 @@
 //               normalise.  LayerNorms are folded into the GEMMs (see drag_gemm.cuh): hidden states
 //               are stored raw (pre-LN, bf16) with per-row (sum, sum^2) partials.
 // All GEMMs are the tcgen05/TMA kernel of drag_gemm.cuh with fused epilogues.
+#include <stdlib.h>
+
 #include <mutex>
 #include <new>
 #include <vector>
 
 #include "drag_attention.cuh"
+#include "drag_attention_tc.cuh"
 #include "drag_common.cuh"
 #include "drag_gemm.cuh"
 
@@ -29,6 +32,7 @@ constexpr int HEAD_DIM = 32;
 constexpr int QKV_BLOCK_N = 192;   // 1152 = 6 x 192
 constexpr int FFN_BLOCK_N = 256;   // 1536 = 6 x 256
 constexpr int RES_BLOCK_N = 128;   // 384 = 3 x 128 (one statistics slot per tile)
+constexpr int RES_BLOCK_N_PAIR = 192;  // CTA-pair kernels: 384 = 2 x 192 (third statistics slot stays zero)
 constexpr int PARTS = gemm::STATS_PARTS;
 
 // ---------------------------------------------------------------------------------
@@ -172,6 +176,7 @@ struct Layer {
   float *down_cold, *down_gamma;       // FFN-down residual: b_down + beta_1, gamma_1 [384]
   float *ln2_g, *ln2_b;                // this layer's output LayerNorm (used by the taps / the pooler)
   CUtensorMap tm_qkv, tm_o, tm_up, tm_down;
+  CUtensorMap tp_qkv, tp_o, tp_up, tp_down;   // CTA-pair kernels: each CTA loads half of a W tile
 };
 
 }  // namespace enc
@@ -194,6 +199,11 @@ struct drag_encoder {
   float2 *stats_x = nullptr, *stats_y = nullptr;  // [T][PARTS] partial (sum, sum^2)
   CUtensorMap tm_x, tm_y, tm_ctx, tm_h;           // A-operand loads (128 x 64 boxes)
   CUtensorMap ts_x, ts_y, ts_qkv, ts_h;           // epilogue stores (32 x 64 boxes)
+  CUtensorMap tm_qkv_heads;                       // attention loads: 128 tokens x one head (32 columns)
+  // cta_group::2 (CTA-pair) GEMMs: bit 0 QKV, 1 out-proj, 2 FFN-up, 3 FFN-down.  Measured on B200: pairs win
+  // where the main loop dominates (K = 1536), single CTAs where the epilogue does (K = 384).  DRAG_GEMM_PAIRS=<mask>.
+  int gemm_pairs = 8;
+  int attention_variant = 0;                      // 0 = mma.sync kernel (default: faster today), 1 = tcgen05 kernel (DRAG_ATTENTION=tc)
   // host-buffer path
   cudaStream_t stream = nullptr;
   int32_t *d_ids = nullptr, *d_cu = nullptr;
@@ -269,11 +279,11 @@ int upload_concat_f32(drag_encoder* e, float** dst, std::initializer_list<const 
   return upload_f32(e, dst, tmp.data(), tmp.size());
 }
 
-template <int BLOCK_N, int EPI, int EPI_WARPS, int STAGES>
+template <int BLOCK_N, int EPI, int EPI_WARPS, int STAGES, int CG>
 int launch_gemm(const drag_encoder* e, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tout,
                 const gemm::GemmParams& p, cudaStream_t st) {
-  auto kern = gemm::gemm_kernel<BLOCK_N, EPI, EPI_WARPS, STAGES>;
-  constexpr size_t smem = gemm::smem_bytes<BLOCK_N, STAGES, EPI_WARPS>();
+  auto kern = gemm::gemm_kernel<BLOCK_N, EPI, EPI_WARPS, STAGES, CG>;
+  constexpr size_t smem = gemm::smem_bytes<BLOCK_N, STAGES, EPI_WARPS, CG>();
   static_assert(smem <= 227 * 1024, "GEMM configuration exceeds the 227 KB shared memory of an SM");
   static std::once_flag once[16];
   static cudaError_t attr_err[16];
@@ -283,18 +293,68 @@ int launch_gemm(const drag_encoder* e, const CUtensorMap& ta, const CUtensorMap&
   });
   if (attr_err[dev_slot] != cudaSuccess)
     return fail(DRAG_ERR_CUDA, "cudaFuncSetAttribute(gemm smem=%zu) failed: %s", smem, cudaGetErrorString(attr_err[dev_slot]));
-  const int m_tiles = (p.M + gemm::BLOCK_M - 1) / gemm::BLOCK_M;
+  const int m_tiles = (p.M + gemm::BLOCK_M * CG - 1) / (gemm::BLOCK_M * CG);
   const int tiles = m_tiles * (p.N / BLOCK_N);
-  const int grid = tiles < e->sms ? tiles : e->sms;
-  kern<<<grid, 64 + 32 * EPI_WARPS, smem, st>>>(ta, tw, tout, p);
+  const int workers = e->sms / CG;   // CTAs, or CTA pairs (one pair per TPC)
+  const int grid = CG * (tiles < workers ? tiles : workers);
+  if (CG == 1) {
+    kern<<<grid, 64 + 32 * EPI_WARPS, smem, st>>>(ta, tw, tout, p);
+    DRAG_CUDA_OK(cudaGetLastError());
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(64 + 32 * EPI_WARPS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DRAG_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tw, tout, p));
+  }
+  return DRAG_OK;
+}
+
+// attention of every (sequence, head) of the packed batch
+int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* qkv, bf16* ctx, const int32_t* d_cu,
+                     int n_seq, int max_len, int heads, cudaStream_t st) {
+  const float scale_log2 = 1.4426950408889634f / sqrtf((float)HEAD_DIM);
+  if (variant == 1) {
+    const size_t smem = attn_tc::smem_bytes(max_len);
+    const int items = heads * n_seq;
+    int sms = 148;
+    {
+      int dev = 0;
+      if (cudaGetDevice(&dev) == cudaSuccess && sm_count(dev) > 0) sms = sm_count(dev);
+    }
+    attn_tc::attention_tc_kernel<<<items < sms ? items : sms, attn_tc::THREADS, smem, st>>>(
+        tm_qkv_heads, ctx, d_cu, n_seq, heads, (max_len + attn_tc::TILE - 1) / attn_tc::TILE, attn_tc::item_stages(max_len), scale_log2);
+  } else {
+    const int s_pad = (max_len + 63) & ~63;
+    const size_t smem = (size_t)2 * s_pad * attn::KV_STRIDE * sizeof(bf16);
+    attn::attention_kernel<<<dim3(heads, n_seq), attn::WARPS * 32, smem, st>>>(qkv, ctx, d_cu, heads * HEAD_DIM, scale_log2);
+  }
   DRAG_CUDA_OK(cudaGetLastError());
   return DRAG_OK;
 }
 
+int attention_set_attributes() {
+  DRAG_CUDA_OK(cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 512 * attn::KV_STRIDE * 2));
+  DRAG_CUDA_OK(cudaFuncSetAttribute(attn_tc::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_tc::smem_bytes(512)));
+  return DRAG_OK;
+}
+
 // the four GEMM configurations of a layer
-#define DRAG_GEMM_QKV  launch_gemm<QKV_BLOCK_N, gemm::EPI_LNIN, 4, 4>
-#define DRAG_GEMM_UP   launch_gemm<FFN_BLOCK_N, gemm::EPI_LNIN_GELU, 8, 3>
-#define DRAG_GEMM_RES  launch_gemm<RES_BLOCK_N, gemm::EPI_RES, 8, 5>
+#define DRAG_GEMM_QKV  launch_gemm<QKV_BLOCK_N, gemm::EPI_LNIN, 4, 4, 1>
+#define DRAG_GEMM_UP   launch_gemm<FFN_BLOCK_N, gemm::EPI_LNIN_GELU, 8, 3, 1>
+#define DRAG_GEMM_RES  launch_gemm<RES_BLOCK_N, gemm::EPI_RES, 8, 5, 1>
+// ... and their CTA-pair (cta_group::2) forms: 256 x BLOCK_N tiles, half a W tile per CTA
+#define DRAG_GEMM2_QKV launch_gemm<QKV_BLOCK_N, gemm::EPI_LNIN, 4, 6, 2>
+#define DRAG_GEMM2_UP  launch_gemm<FFN_BLOCK_N, gemm::EPI_LNIN_GELU, 8, 5, 2>
+#define DRAG_GEMM2_RES launch_gemm<RES_BLOCK_N_PAIR, gemm::EPI_RES, 12, 6, 2>
 
 int forward_impl(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu, const int32_t* h_cu, int n_seq,
                  float* d_out, int stop_after_layer, float* d_hidden, cudaStream_t st) {
@@ -322,9 +382,6 @@ int forward_impl(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu, con
     DRAG_CUDA_OK(cudaGetLastError());
   }
   const int n_layers = (tap && stop_after_layer < sh.layers) ? stop_after_layer : sh.layers;
-  const float scale_log2 = 1.4426950408889634f / sqrtf((float)HEAD_DIM);
-  const int s_pad = (max_len + 63) & ~63;
-  const size_t attn_smem = (size_t)2 * s_pad * attn::KV_STRIDE * sizeof(bf16);
   for (int l = 0; l < n_layers; ++l) {
     const Layer& L = e->layers[l];
     gemm::GemmParams p{};
@@ -336,21 +393,21 @@ int forward_impl(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu, con
     p.N = 3 * HIDDEN; p.K = HIDDEN; p.colc = L.qkv_c; p.cold = L.qkv_d; p.in_stats = e->stats_x;
     {
       ProfScope prof(e, KC_GEMM_QKV, st);
-      rc = DRAG_GEMM_QKV(e, e->tm_x, L.tm_qkv, e->ts_qkv, p, st);
+      rc = (e->gemm_pairs & 1) ? DRAG_GEMM2_QKV(e, e->tm_x, L.tp_qkv, e->ts_qkv, p, st) : DRAG_GEMM_QKV(e, e->tm_x, L.tm_qkv, e->ts_qkv, p, st);
     }
     if (rc) return rc;
     // attention
     {
       ProfScope prof(e, KC_ATTENTION, st);
-      attn::attention_kernel<<<dim3(sh.heads, n_seq), attn::WARPS * 32, attn_smem, st>>>(e->qkv, e->ctx, d_cu, HIDDEN, scale_log2);
+      rc = launch_attention(e->attention_variant, e->tm_qkv_heads, e->qkv, e->ctx, d_cu, n_seq, max_len, sh.heads, st);
     }
-    DRAG_CUDA_OK(cudaGetLastError());
+    if (rc) return rc;
     // y_raw = ctx . Wo^T + b_o + LN_in(x_raw)   (+ row statistics of y_raw)
     p.N = HIDDEN; p.K = HIDDEN; p.colc = nullptr; p.cold = L.o_cold; p.gamma = L.o_gamma; p.in_stats = e->stats_x;
     p.residual = e->x; p.out_stats = e->stats_y;
     {
       ProfScope prof(e, KC_GEMM_OUT_LN, st);
-      rc = DRAG_GEMM_RES(e, e->tm_ctx, L.tm_o, e->ts_y, p, st);
+      rc = (e->gemm_pairs & 2) ? DRAG_GEMM2_RES(e, e->tm_ctx, L.tp_o, e->ts_y, p, st) : DRAG_GEMM_RES(e, e->tm_ctx, L.tm_o, e->ts_y, p, st);
     }
     if (rc) return rc;
     // h = gelu(LN_1(y) . W1^T + b_1)
@@ -358,7 +415,7 @@ int forward_impl(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu, con
     p.residual = nullptr; p.out_stats = nullptr;
     {
       ProfScope prof(e, KC_GEMM_UP_GELU, st);
-      rc = DRAG_GEMM_UP(e, e->tm_y, L.tm_up, e->ts_h, p, st);
+      rc = (e->gemm_pairs & 4) ? DRAG_GEMM2_UP(e, e->tm_y, L.tp_up, e->ts_h, p, st) : DRAG_GEMM_UP(e, e->tm_y, L.tm_up, e->ts_h, p, st);
     }
     if (rc) return rc;
     // x_raw = h . W2^T + b_2 + LN_1(y_raw)   (+ row statistics of x_raw); LN_2 is applied by the consumers
@@ -366,7 +423,7 @@ int forward_impl(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu, con
     p.residual = e->y; p.out_stats = e->stats_x;
     {
       ProfScope prof(e, KC_GEMM_DOWN_LN, st);
-      rc = DRAG_GEMM_RES(e, e->tm_h, L.tm_down, e->ts_x, p, st);
+      rc = (e->gemm_pairs & 8) ? DRAG_GEMM2_RES(e, e->tm_h, L.tp_down, e->ts_x, p, st) : DRAG_GEMM_RES(e, e->tm_h, L.tm_down, e->ts_x, p, st);
     }
     if (rc) return rc;
   }
@@ -484,6 +541,10 @@ extern "C" int drag_encoder_create(const drag_bert_shape* shape, const float* co
     if ((rc = make_tmap(&L.tm_o, L.w_o, H, H, RES_BLOCK_N))) return bail(rc);
     if ((rc = make_tmap(&L.tm_up, L.w_up, F, H, FFN_BLOCK_N))) return bail(rc);
     if ((rc = make_tmap(&L.tm_down, L.w_down, H, F, RES_BLOCK_N))) return bail(rc);
+    if ((rc = make_tmap(&L.tp_qkv, L.w_qkv, 3 * H, H, QKV_BLOCK_N / 2))) return bail(rc);
+    if ((rc = make_tmap(&L.tp_o, L.w_o, H, H, RES_BLOCK_N_PAIR / 2))) return bail(rc);
+    if ((rc = make_tmap(&L.tp_up, L.w_up, F, H, FFN_BLOCK_N / 2))) return bail(rc);
+    if ((rc = make_tmap(&L.tp_down, L.w_down, H, F, RES_BLOCK_N_PAIR / 2))) return bail(rc);
   }
   const size_t T = (size_t)e->max_tokens;
   if ((rc = dev_alloc(e, &e->x, T * H))) return bail(rc);
@@ -505,6 +566,13 @@ extern "C" int drag_encoder_create(const drag_bert_shape* shape, const float* co
   if ((rc = make_tmap(&e->ts_y, e->y, T, H, gemm::STORE_ROWS))) return bail(rc);
   if ((rc = make_tmap(&e->ts_qkv, e->qkv, T, 3 * H, gemm::STORE_ROWS))) return bail(rc);
   if ((rc = make_tmap(&e->ts_h, e->h, T, F, gemm::STORE_ROWS))) return bail(rc);
+  if ((rc = make_tmap_bf16_box(&e->tm_qkv_heads, e->qkv, T, 3 * H, attn_tc::TILE, attn_tc::HEAD_DIM))) return bail(rc);
+  {
+    const char* v = getenv("DRAG_ATTENTION");
+    if (v && strcmp(v, "tc") == 0) e->attention_variant = 1;
+    const char* gm = getenv("DRAG_GEMM_PAIRS");
+    if (gm && gm[0] >= '0' && gm[0] <= '9') e->gemm_pairs = atoi(gm) & 15;
+  }
 
   // host-buffer path: pinned staging + device mirrors
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(DRAG_ERR_CUDA, "cudaStreamCreate failed"));
@@ -512,9 +580,8 @@ extern "C" int drag_encoder_create(const drag_bert_shape* shape, const float* co
   if ((rc = dev_alloc(e, &e->d_cu, T + 1))) return bail(rc);
   if (cudaMallocHost((void**)&e->p_ids, T * 4) != cudaSuccess || cudaMallocHost((void**)&e->p_cu, (T + 1) * 4) != cudaSuccess)
     return bail(fail(DRAG_ERR_NOMEM, "cudaMallocHost failed"));
-  // attention kernel may need > 48 KB of dynamic shared memory (512-token sequences: 80 KB)
-  if (cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 512 * attn::KV_STRIDE * 2) != cudaSuccess)
-    return bail(fail(DRAG_ERR_CUDA, "cudaFuncSetAttribute(attention) failed: %s", cudaGetErrorString(cudaGetLastError())));
+  // the attention kernels need > 48 KB of dynamic shared memory
+  if ((rc = attention_set_attributes())) return bail(rc);
   if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(DRAG_ERR_CUDA, "weight upload failed: %s", cudaGetErrorString(cudaGetLastError())));
   *out = e;
   return DRAG_OK;
@@ -627,25 +694,37 @@ extern "C" int drag_debug_gemm(int device, int variant, const void* d_a, const v
       DRAG_REQUIRE(N == HIDDEN && d_gamma && d_residual && d_out_stats, "drag_debug_gemm: variant 2 needs N=384, gamma, residual, out_stats");
       if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, RES_BLOCK_N))) return rc;
       return DRAG_GEMM_RES(&fake, ta, tw, tout, p, st);
+    case 10:
+      DRAG_REQUIRE(N % QKV_BLOCK_N == 0 && d_colc, "drag_debug_gemm: variant 10 needs N %% %d == 0 and colc", QKV_BLOCK_N);
+      if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, QKV_BLOCK_N / 2))) return rc;
+      return DRAG_GEMM2_QKV(&fake, ta, tw, tout, p, st);
+    case 11:
+      DRAG_REQUIRE(N % FFN_BLOCK_N == 0 && d_colc, "drag_debug_gemm: variant 11 needs N %% %d == 0 and colc", FFN_BLOCK_N);
+      if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, FFN_BLOCK_N / 2))) return rc;
+      return DRAG_GEMM2_UP(&fake, ta, tw, tout, p, st);
+    case 12:
+      DRAG_REQUIRE(N == HIDDEN && d_gamma && d_residual && d_out_stats, "drag_debug_gemm: variant 12 needs N=384, gamma, residual, out_stats");
+      if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, RES_BLOCK_N_PAIR / 2))) return rc;
+      return DRAG_GEMM2_RES(&fake, ta, tw, tout, p, st);
     default:
       return fail(DRAG_ERR_INVALID, "drag_debug_gemm: unknown variant %d", variant);
   }
 }
 
-extern "C" int drag_debug_attention(int device, const void* d_qkv, void* d_ctx, const int32_t* d_cu_seqlens, int n_seq,
-                                    int max_len, int heads, void* stream) {
-  DRAG_REQUIRE(d_qkv && d_ctx && d_cu_seqlens && n_seq >= 1 && heads >= 1, "drag_debug_attention: bad arguments");
+extern "C" int drag_debug_attention(int device, int variant, const void* d_qkv, void* d_ctx, const int32_t* d_cu_seqlens,
+                                    int n_seq, int n_tokens, int max_len, int heads, void* stream) {
+  DRAG_REQUIRE(d_qkv && d_ctx && d_cu_seqlens && n_seq >= 1 && heads >= 1 && n_tokens >= 1, "drag_debug_attention: bad arguments");
   DRAG_REQUIRE(max_len >= 1 && max_len <= 512, "drag_debug_attention: max_len must be in 1..512");
+  DRAG_REQUIRE(variant == 0 || variant == 1, "drag_debug_attention: variant 0 (mma.sync) or 1 (tcgen05)");
   DeviceGuard guard(device);
   if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_debug_attention: cannot select device %d", device);
-  DRAG_CUDA_OK(cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 512 * attn::KV_STRIDE * 2));
-  const int s_pad = (max_len + 63) & ~63;
-  const size_t smem = (size_t)2 * s_pad * attn::KV_STRIDE * sizeof(bf16);
-  const float scale_log2 = 1.4426950408889634f / sqrtf((float)HEAD_DIM);
-  attn::attention_kernel<<<dim3(heads, n_seq), attn::WARPS * 32, smem, (cudaStream_t)stream>>>(
-      (const bf16*)d_qkv, (bf16*)d_ctx, d_cu_seqlens, heads * HEAD_DIM, scale_log2);
-  DRAG_CUDA_OK(cudaGetLastError());
-  return DRAG_OK;
+  int rc = attention_set_attributes();
+  if (rc) return rc;
+  CUtensorMap tm;
+  if (variant == 1 &&
+      (rc = make_tmap_bf16_box(&tm, d_qkv, (uint64_t)n_tokens, (uint64_t)3 * heads * HEAD_DIM, attn_tc::TILE, attn_tc::HEAD_DIM)))
+    return rc;
+  return launch_attention(variant, tm, (const bf16*)d_qkv, (bf16*)d_ctx, d_cu_seqlens, n_seq, max_len, heads, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------

@@ -17,6 +17,11 @@
 //     EPI_RES        out = acc + cold + LN(residual_raw)  (raw, pre-LN) and the row's partial
 //                    (sum, sum^2) over this tile's columns -> out_stats   (attention out / FFN down)
 //
+// CG = 2 runs the same pipeline on CTA PAIRS (tcgen05 cta_group::2): a pair owns a 256 x BLOCK_N tile,
+// each CTA stages its own 128 rows of A and HALF of the W tile (BLOCK_N/2 rows), the leader issues
+// M=256 MMAs that read both halves, and each CTA drains its own 128 accumulator rows.  Operand bytes
+// per flop drop by a third or more, which is what bounds the K=384 GEMMs (L2 -> SM traffic).
+//
 // CTA = 2 + EPI_WARPS warps, one CTA per SM, looping over 128 x BLOCK_N output tiles:
 //   warp 0   TMA producer (cp.async.bulk.tensor, 128B swizzle) into a STAGES-deep smem ring
 //   warp 1   MMA issuer: one thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) per k-step;
@@ -64,13 +69,13 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "invalid UMMA N");
   static_assert(2 * BLOCK_N <= 512, "accumulator must double-buffer in 512 TMEM columns");
-  static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024-byte alignment");
+  static_assert(STAGE_BYTES % 1024 == 0 && (B_STAGE_BYTES / 2) % 1024 == 0, "stage must keep 1024-byte alignment");
 };
 
-template <int BLOCK_N, int STAGES, int EPI_WARPS>
+template <int BLOCK_N, int STAGES, int EPI_WARPS, int CG = 1>
 constexpr size_t smem_bytes() {
   // ring + per-warp store staging + barriers/tmem pointer + slack for manual 1024-byte alignment
-  return (size_t)STAGES * Cfg<BLOCK_N>::STAGE_BYTES + (size_t)EPI_WARPS * STAGING_BYTES + 2048 + 1024;
+  return (size_t)STAGES * (A_STAGE_BYTES + Cfg<BLOCK_N>::B_STAGE_BYTES / CG) + (size_t)EPI_WARPS * STAGING_BYTES + 4096 + 1024;
 }
 
 // GELU(x) = x * Phi(x) with Phi(x) ~ 0.5 * (1 + tanh(x * (c0 + c1 x^2 + c2 x^4))): minimax fit on
@@ -104,12 +109,17 @@ __device__ __forceinline__ void row_stats(const float2* stats, int row, bool ok,
   rstd = rsqrtf(fmaxf(ss * inv_width - mu * mu, 0.f) + eps);
 }
 
-template <int BLOCK_N, int EPI, int EPI_WARPS, int STAGES>
+template <int BLOCK_N, int EPI, int EPI_WARPS, int STAGES, int CG>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
             const __grid_constant__ CUtensorMap tmap_out, GemmParams p) {
   using C = Cfg<BLOCK_N>;
-  static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "epilogue uses 4 or 8 warps");
+  static_assert(CG == 1 || CG == 2, "single CTAs or CTA pairs");
+  constexpr int B_BYTES = C::B_STAGE_BYTES / CG;          // this CTA's part of the W tile
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_BYTES;
+  constexpr int TILE_M = BLOCK_M * CG;
+  static_assert(EPI_WARPS % 4 == 0 && EPI_WARPS >= 4 && EPI_WARPS <= 16, "epilogue warps come in groups of 4 (one per TMEM lane quarter)");
+  static_assert(EPI != EPI_RES || EPI_WARPS <= 12, "the statistics exchange of EPI_RES handles at most three column groups");
   constexpr int COL_GROUPS = EPI_WARPS / 4;
   constexpr int COLS_PER_THREAD = BLOCK_N / COL_GROUPS;
   static_assert(COLS_PER_THREAD % STORE_COLS == 0, "epilogue stores 64-column groups");
@@ -117,7 +127,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = smem;
-  uint8_t* staging = smem + (size_t)STAGES * C::STAGE_BYTES;  // 1024-aligned, 4 KB per epilogue warp
+  uint8_t* staging = smem + (size_t)STAGES * STAGE_BYTES;  // 1024-aligned, 4 KB per epilogue warp
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + (size_t)EPI_WARPS * STAGING_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
@@ -127,9 +137,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles = p.N / BLOCK_N;
-  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int m_tiles = (p.M + TILE_M - 1) / TILE_M;
   const int num_tiles = m_tiles * n_tiles;
   const int k_blocks = p.K / BLOCK_K;
+  const uint32_t cta_rank = CG == 2 ? tc::cluster_ctarank() : 0u;   // 0 = pair leader
+  const int worker = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_workers = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmap_a);
@@ -141,13 +154,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&tmem_full_bar[s], 1);
-      tc::mbar_init(&tmem_empty_bar[s], EPI_WARPS);
+      tc::mbar_init(&tmem_empty_bar[s], CG * EPI_WARPS);   // the leader's collects both CTAs' epilogue warps
     }
     tc::fence_barrier_init();
   }
+  if (CG == 2) tc::cluster_sync_all();   // the peer's barriers must exist before anything signals them
   if (warp == 1) {
-    tc::tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
-    tc::tmem_relinquish();
+    if (CG == 2) {
+      tc::tmem_alloc_pair(tmem_ptr_smem, C::TMEM_COLS);
+      tc::tmem_relinquish_pair();
+    } else {
+      tc::tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
+      tc::tmem_relinquish();
+    }
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -159,14 +178,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += n_workers) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         for (int kb = 0; kb < k_blocks; ++kb) {
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* a_dst = ring + (size_t)stage * C::STAGE_BYTES;
-          tc::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-          tc::tma_load_2d(&tmap_a, &full_bar[stage], a_dst, kb * BLOCK_K, m_blk * BLOCK_M);
-          tc::tma_load_2d(&tmap_w, &full_bar[stage], a_dst + A_STAGE_BYTES, kb * BLOCK_K, n_blk * BLOCK_N);
+          uint8_t* a_dst = ring + (size_t)stage * STAGE_BYTES;
+          if (CG == 2) {
+            // both CTAs load their halves; all bytes are credited to the LEADER's full barrier
+            if (cta_rank == 0) tc::mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+            const uint32_t bar = tc::mapa_shared(tc::smem_u32(&full_bar[stage]), 0);
+            tc::tma_load_2d_pair(&tmap_a, bar, a_dst, kb * BLOCK_K, m_blk * TILE_M + (int)cta_rank * BLOCK_M);
+            tc::tma_load_2d_pair(&tmap_w, bar, a_dst + A_STAGE_BYTES, kb * BLOCK_K, n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / 2));
+          } else {
+            tc::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+            tc::tma_load_2d(&tmap_a, &full_bar[stage], a_dst, kb * BLOCK_K, m_blk * BLOCK_M);
+            tc::tma_load_2d(&tmap_w, &full_bar[stage], a_dst + A_STAGE_BYTES, kb * BLOCK_K, n_blk * BLOCK_N);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -174,31 +201,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::umma_idesc_bf16(BLOCK_M, BLOCK_N);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = tc::umma_idesc_bf16(TILE_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += n_workers) {
         tc::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
         for (int kb = 0; kb < k_blocks; ++kb) {
           tc::mbar_wait(&full_bar[stage], phase);
           tc::tc_fence_after();
-          const uint32_t a_addr = tc::smem_u32(ring + (size_t)stage * C::STAGE_BYTES);
+          const uint32_t a_addr = tc::smem_u32(ring + (size_t)stage * STAGE_BYTES);
           const uint64_t a_desc = tc::umma_desc_sw128(a_addr);
           const uint64_t b_desc = tc::umma_desc_sw128(a_addr + A_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // +32 bytes per 16-element k-step inside the 128-byte swizzle row (encoded >> 4)
-            tc::umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CG == 2) tc::umma_bf16_pair(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            else tc::umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tc::umma_commit(&empty_bar[stage]);  // ring slot reusable once these MMAs retire
+          // ring slot reusable (in both CTAs of a pair) once these MMAs retire
+          if (CG == 2) tc::umma_commit_pair(&empty_bar[stage], 3);
+          else tc::umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc::umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if (CG == 2) tc::umma_commit_pair(&tmem_full_bar[acc], 3);
+        else tc::umma_commit(&tmem_full_bar[acc]);
         if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -213,9 +245,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const uint32_t stage_row = tc::smem_u32(stage_buf) + (uint32_t)lane * 128u;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const uint32_t leader_tmem_empty = CG == 2 ? tc::mapa_shared(tc::smem_u32(&tmem_empty_bar[0]), 0) : 0u;
+    for (int tile = worker; tile < num_tiles; tile += n_workers) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-      const int row = m_blk * BLOCK_M + row_in_tile;
+      const int row0 = m_blk * TILE_M + (int)cta_rank * BLOCK_M;   // first row of this CTA's 128-row slab
+      const int row = row0 + row_in_tile;
       const bool row_ok = row < p.M;
       const int col0 = n_blk * BLOCK_N + col_group * COLS_PER_THREAD;
       float mu, rstd;
@@ -295,27 +329,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         tc::fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          tc::tma_store_2d(&tmap_out, stage_buf, col0 + g, m_blk * BLOCK_M + quarter * 32);
+          tc::tma_store_2d(&tmap_out, stage_buf, col0 + g, row0 + quarter * 32);
           tc::tma_store_commit();
         }
       }
       // all TMEM reads of this warp are complete -> hand the accumulator back to the MMA warp
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[acc]);
+      if (lane == 0) {
+        if (CG == 2) tc::mbar_arrive_cluster(leader_tmem_empty + (uint32_t)(acc * 8));
+        else tc::mbar_arrive(&tmem_empty_bar[acc]);
+      }
       if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
 
       if (EPI == EPI_RES) {
         if (COL_GROUPS == 1) {
           if (row_ok) p.out_stats[(size_t)row * STATS_PARTS + n_blk] = make_float2(s_sum, s_sq);
         } else {
-          // two warps share a row (column halves): combine through shared memory in a fixed order
-          float2* part = reinterpret_cast<float2*>(tmem_ptr_smem + 4);  // [128]
-          if (col_group == 1) part[row_in_tile] = make_float2(s_sum, s_sq);
+          // several warps share a row (column groups): combine through shared memory in a fixed order
+          float2* part = reinterpret_cast<float2*>(tmem_ptr_smem + 4);  // [COL_GROUPS - 1][128]
+          if (col_group > 0) part[(col_group - 1) * BLOCK_M + row_in_tile] = make_float2(s_sum, s_sq);
           asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
           if (col_group == 0 && row_ok) {
-            const float2 o2 = part[row_in_tile];
-            p.out_stats[(size_t)row * STATS_PARTS + n_blk] = make_float2(s_sum + o2.x, s_sq + o2.y);
+#pragma unroll
+            for (int cg = 1; cg < COL_GROUPS; ++cg) {
+              const float2 o2 = part[(cg - 1) * BLOCK_M + row_in_tile];
+              s_sum += o2.x;
+              s_sq += o2.y;
+            }
+            p.out_stats[(size_t)row * STATS_PARTS + n_blk] = make_float2(s_sum, s_sq);
           }
           asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
         }
@@ -326,9 +368,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   tc::tc_fence_before();
   __syncthreads();
+  if (CG == 2) tc::cluster_sync_all();   // the peer may still signal this CTA's barriers / read its operands
   if (warp == 1) {
     tc::tc_fence_after();
-    tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (CG == 2) tc::tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+    else tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 

@@ -79,7 +79,7 @@ _SIGNATURES = {
     "drag_rows_to_chunks": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, _P, _P, _P]),
     "drag_debug_gemm": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int,
                                   C.c_float, C.c_float, _P]),
-    "drag_debug_attention": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "drag_debug_attention": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

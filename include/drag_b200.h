@@ -242,9 +242,10 @@ int drag_debug_gemm(int device, int variant, const void* d_a, const void* d_w, c
                     void* d_out, void* d_out_stats, int M, int N, int K, float inv_width, float ln_eps,
                     void* stream);
 
-/* ctx[T, heads*32] = softmax(Q K^T / sqrt(32)) V per packed sequence; d_qkv is bf16 [T, 3*heads*32]. */
-int drag_debug_attention(int device, const void* d_qkv, void* d_ctx, const int32_t* d_cu_seqlens,
-                         int n_seq, int max_len, int heads, void* stream);
+/* ctx[T, heads*32] = softmax(Q K^T / sqrt(32)) V per packed sequence; d_qkv is bf16 [n_tokens, 3*heads*32].
+ * variant 0 = mma.sync kernel (the encoder's default), 1 = tcgen05 kernel (DRAG_ATTENTION=tc). */
+int drag_debug_attention(int device, int variant, const void* d_qkv, void* d_ctx, const int32_t* d_cu_seqlens,
+                         int n_seq, int n_tokens, int max_len, int heads, void* stream);
 
 /*
  * Approximate "bigger is better" keys of the batched path's score kernel for every (query, row):

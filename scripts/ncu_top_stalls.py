@@ -1,13 +1,14 @@
-"""Print the SASS instructions with the most warp-stall samples from `ncu --page source --csv` output."""
+"""Top SASS instructions by warp-stall samples from `ncu -i rep --page source --csv` output."""
 import csv
 import sys
 
-path, n = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 40
-rows = list(csv.reader(open(path)))
-print(rows[0][1][:150])
-data = rows[2:]
-tot = sum(int(r[2]) for r in data if r[2].isdigit())
+rows = list(csv.reader(open(sys.argv[1])))
+hdr = rows[1]
+si, src, ex = hdr.index("# Samples"), hdr.index("Source"), hdr.index("Instructions Executed")
+body = rows[2:]
+tot = sum(int(r[si] or 0) for r in body)
+top = sorted(range(len(body)), key=lambda i: -int(body[i][si] or 0))[: int(sys.argv[2]) if len(sys.argv) > 2 else 25]
 print("total samples", tot)
-top = sorted([(int(r[2]), i, r[1].strip()) for i, r in enumerate(data) if r[2].isdigit()], reverse=True)[:n]
-for s, i, src in sorted(top, key=lambda t: t[1]):
-    print(f"{i:5d} {s:6d} {100 * s / tot:5.1f}%  {src[:120]}")
+for i in sorted(top):
+    r = body[i]
+    print(f"{i:5d} {int(r[si]):6d} {100 * int(r[si]) / tot:5.1f}%  exec={r[ex]:>9s} {r[src].strip()[:110]}")
