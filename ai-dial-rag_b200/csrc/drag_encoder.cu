@@ -200,9 +200,10 @@ struct drag_encoder {
   CUtensorMap tm_x, tm_y, tm_ctx, tm_h;           // A-operand loads (128 x 64 boxes)
   CUtensorMap ts_x, ts_y, ts_qkv, ts_h;           // epilogue stores (32 x 64 boxes)
   CUtensorMap tm_qkv_heads;                       // attention loads: 128 tokens x one head (32 columns)
-  // cta_group::2 (CTA-pair) GEMMs: bit 0 QKV, 1 out-proj, 2 FFN-up, 3 FFN-down.  Measured on B200: pairs win
-  // where the main loop dominates (K = 1536), single CTAs where the epilogue does (K = 384).  DRAG_GEMM_PAIRS=<mask>.
-  int gemm_pairs = 8;
+  // cta_group::2 (CTA-pair) GEMMs: bit 0 QKV, 1 out-proj, 2 FFN-up, 3 FFN-down.  Measured on B200 (same run,
+  // 262144 tokens): QKV 0.255 vs 0.267 ms, FFN-up 0.365 vs 0.375, FFN-down 0.339 vs 0.397 in favour of pairs;
+  // the out-projection (N = K = 384, epilogue-bound) 0.178 vs 0.202 in favour of single CTAs.  DRAG_GEMM_PAIRS=<mask>.
+  int gemm_pairs = 13;
   int attention_variant = 0;                      // 0 = mma.sync kernel (default: faster today), 1 = tcgen05 kernel (DRAG_ATTENTION=tc)
   // host-buffer path
   cudaStream_t stream = nullptr;
@@ -353,7 +354,7 @@ int attention_set_attributes() {
 #define DRAG_GEMM_RES  launch_gemm<RES_BLOCK_N, gemm::EPI_RES, 8, 5, 1>
 // ... and their CTA-pair (cta_group::2) forms: 256 x BLOCK_N tiles, half a W tile per CTA
 #define DRAG_GEMM2_QKV launch_gemm<QKV_BLOCK_N, gemm::EPI_LNIN, 4, 6, 2>
-#define DRAG_GEMM2_UP  launch_gemm<FFN_BLOCK_N, gemm::EPI_LNIN_GELU, 8, 5, 2>
+#define DRAG_GEMM2_UP  launch_gemm<FFN_BLOCK_N, gemm::EPI_LNIN_GELU, 8, 4, 2>
 #define DRAG_GEMM2_RES launch_gemm<RES_BLOCK_N_PAIR, gemm::EPI_RES, 12, 6, 2>
 
 int forward_impl(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu, const int32_t* h_cu, int n_seq,

@@ -72,10 +72,15 @@ struct Cfg {
   static_assert(STAGE_BYTES % 1024 == 0 && (B_STAGE_BYTES / 2) % 1024 == 0, "stage must keep 1024-byte alignment");
 };
 
+template <int BLOCK_N, int EPI_WARPS>
+constexpr int stage_bufs() { return (BLOCK_N / (EPI_WARPS / 4)) > STORE_COLS ? 2 : 1; }
+
 template <int BLOCK_N, int STAGES, int EPI_WARPS, int CG = 1>
 constexpr size_t smem_bytes() {
-  // ring + per-warp store staging + barriers/tmem pointer + slack for manual 1024-byte alignment
-  return (size_t)STAGES * (A_STAGE_BYTES + Cfg<BLOCK_N>::B_STAGE_BYTES / CG) + (size_t)EPI_WARPS * STAGING_BYTES + 4096 + 1024;
+  // ring + per-warp store staging + [barriers, tmem pointer, statistics exchange | 4 KB] + [column constants:
+  // 2 tiles x 2 vectors x BLOCK_N floats <= 4 KB] + slack for manual 1024-byte alignment
+  return (size_t)STAGES * (A_STAGE_BYTES + Cfg<BLOCK_N>::B_STAGE_BYTES / CG) +
+         (size_t)EPI_WARPS * stage_bufs<BLOCK_N, EPI_WARPS>() * STAGING_BYTES + 8192 + 1024;
 }
 
 // GELU(x) = x * Phi(x) with Phi(x) ~ 0.5 * (1 + tanh(x * (c0 + c1 x^2 + c2 x^4))): minimax fit on
@@ -122,13 +127,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   static_assert(EPI != EPI_RES || EPI_WARPS <= 12, "the statistics exchange of EPI_RES handles at most three column groups");
   constexpr int COL_GROUPS = EPI_WARPS / 4;
   constexpr int COLS_PER_THREAD = BLOCK_N / COL_GROUPS;
+  constexpr int STAGE_BUFS = stage_bufs<BLOCK_N, EPI_WARPS>();   // a warp with several store groups per tile double buffers
   static_assert(COLS_PER_THREAD % STORE_COLS == 0, "epilogue stores 64-column groups");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = smem;
   uint8_t* staging = smem + (size_t)STAGES * STAGE_BYTES;  // 1024-aligned, 4 KB per epilogue warp
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + (size_t)EPI_WARPS * STAGING_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + (size_t)EPI_WARPS * STAGE_BUFS * STAGING_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -237,15 +243,52 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     __syncwarp();
   } else {
     // ===================== epilogue =====================
+    // Latency is hidden across tiles and chunks: the row statistics and the per-column constants of
+    // the NEXT tile are fetched while the current one is processed (registers / cp.async into a
+    // double-buffered shared-memory table), the TMEM load of the next 32 columns is in flight during
+    // the math of the current 32, and store staging is double buffered.
     const int ew = warp - 2;
+    const int et = ew * 32 + lane;          // index among the epilogue threads
     const int quarter = warp & 3;           // TMEM lanes this warp may touch: [32*quarter, +32)
     const int col_group = ew >> 2;
     const int row_in_tile = quarter * 32 + lane;
-    uint8_t* stage_buf = staging + (size_t)ew * STAGING_BYTES;
+    uint8_t* stage_buf = staging + (size_t)ew * (STAGE_BUFS * STAGING_BYTES);
     const uint32_t stage_row = tc::smem_u32(stage_buf) + (uint32_t)lane * 128u;
+    float* coltab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 4096);  // [2][2][BLOCK_N], second 4 KB of the region
+    const float* col_v0 = EPI == EPI_RES ? p.gamma : p.colc;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int par = 0, sbuf = 0;
     const uint32_t leader_tmem_empty = CG == 2 ? tc::mapa_shared(tc::smem_u32(&tmem_empty_bar[0]), 0) : 0u;
+
+    auto fetch_cols = [&](int tile_, int par_) {
+      // BLOCK_N/4 16-byte chunks of each of the two column vectors of the tile's column block
+      const int n_blk_ = tile_ % n_tiles;
+      if (et < BLOCK_N / 2) {
+        const bool second = et >= BLOCK_N / 4;
+        const int chunk = second ? et - BLOCK_N / 4 : et;
+        const float* src = (second ? p.cold : col_v0) + n_blk_ * BLOCK_N + chunk * 4;
+        const uint32_t dst = tc::smem_u32(coltab + (par_ * 2 + (second ? 1 : 0)) * BLOCK_N + chunk * 4);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto fetch_stats = [&](int tile_, float2 (&st)[STATS_PARTS]) {
+      const int row_ = (tile_ / n_tiles) * TILE_M + (int)cta_rank * BLOCK_M + row_in_tile;
+      // volatile asm: the loads must be ISSUED here (a tile ahead of their use), not sunk to the use
+#pragma unroll
+      for (int i = 0; i < STATS_PARTS; ++i) {
+        st[i] = make_float2(0.f, 0.f);
+        if (row_ < p.M)
+          asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(st[i].x), "=f"(st[i].y) : "l"(p.in_stats + (size_t)row_ * STATS_PARTS + i));
+      }
+    };
+
+    float2 next_stats[STATS_PARTS];
+    if (worker < num_tiles) {
+      fetch_cols(worker, 0);
+      fetch_stats(worker, next_stats);
+    }
     for (int tile = worker; tile < num_tiles; tile += n_workers) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int row0 = m_blk * TILE_M + (int)cta_rank * BLOCK_M;   // first row of this CTA's 128-row slab
@@ -253,84 +296,122 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const bool row_ok = row < p.M;
       const int col0 = n_blk * BLOCK_N + col_group * COLS_PER_THREAD;
       float mu, rstd;
-      row_stats(p.in_stats, row, row_ok, p.inv_width, p.ln_eps, mu, rstd);
+      {
+        float s = 0.f, ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < STATS_PARTS; ++i) { s += next_stats[i].x; ss += next_stats[i].y; }
+        mu = s * p.inv_width;
+        rstd = rsqrtf(fmaxf(ss * p.inv_width - mu * mu, 0.f) + p.ln_eps);
+      }
+      // this tile's column constants are in coltab[par]; everybody is done with coltab[par ^ 1]
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      if (tile + n_workers < num_tiles) {
+        fetch_cols(tile + n_workers, par ^ 1);
+        fetch_stats(tile + n_workers, next_stats);
+      }
+      const float* tab0 = coltab + (par * 2) * BLOCK_N + col_group * COLS_PER_THREAD;
+      const float* tab1 = tab0 + BLOCK_N;
       float s_sum = 0.f, s_sq = 0.f;
 
       tc::mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + col_group * COLS_PER_THREAD);
 
-#pragma unroll 1
-      for (int g = 0; g < COLS_PER_THREAD; g += STORE_COLS) {
+      constexpr int N_CHUNKS = COLS_PER_THREAD / 32;
+      uint32_t r[32], r_next[32];
+      uint4 rv[4], rv_next[4];
+      const uint4* res_row = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.N + col0);
+      tc::tmem_ld32(t_row, r);
+      if (EPI == EPI_RES) {
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int c = g + half * 32;
-          uint32_t r[32];
-          tc::tmem_ld32(t_row + c, r);
-          uint32_t o[16];
+        for (int i = 0; i < 4; ++i) rv[i] = row_ok ? __ldg(res_row + i) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int ch = 0; ch < N_CHUNKS; ++ch) {
+        const int c = ch * 32;
+        const int half = ch & 1;
+        tc::tmem_ld_wait();
+        if (ch + 1 < N_CHUNKS) {
+          // next 32 columns: in flight during this chunk's math
+          tc::tmem_ld32(t_row + c + 32, r_next);
           if (EPI == EPI_RES) {
-            uint4 rv[4];
-            const uint4* res = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.N + col0 + c);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) rv[i] = row_ok ? __ldg(res + i) : make_uint4(0, 0, 0, 0);
-            const uint32_t* rw = reinterpret_cast<const uint32_t*>(rv);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + c) + i);
-              const float4 cd = __ldg(reinterpret_cast<const float4*>(p.cold + col0 + c) + i);
-              const float g4[4] = {ga.x, ga.y, ga.z, ga.w};
-              const float d4[4] = {cd.x, cd.y, cd.z, cd.w};
-              float v[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int e = 4 * i + j;
-                const uint32_t w = rw[e >> 1];
-                const float res_raw = (e & 1) ? __uint_as_float(w & 0xffff0000u) : __uint_as_float(w << 16);
-                const float a = g4[j] * rstd;
-                v[j] = fmaf(res_raw - mu, a, __uint_as_float(r[e]) + d4[j]);
-                s_sum += v[j];
-                s_sq = fmaf(v[j], v[j], s_sq);
-              }
-              o[2 * i] = pack_bf16(v[0], v[1]);
-              o[2 * i + 1] = pack_bf16(v[2], v[3]);
-            }
-          } else {
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 cc = __ldg(reinterpret_cast<const float4*>(p.colc + col0 + c) + i);
-              const float4 cd = __ldg(reinterpret_cast<const float4*>(p.cold + col0 + c) + i);
-              const float c4[4] = {cc.x, cc.y, cc.z, cc.w};
-              const float d4[4] = {cd.x, cd.y, cd.z, cd.w};
-              float v[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                v[j] = fmaf(rstd, fmaf(-mu, c4[j], __uint_as_float(r[4 * i + j])), d4[j]);
-                if (EPI == EPI_LNIN_GELU) v[j] = gelu_fast(v[j]);
-              }
-              o[2 * i] = pack_bf16(v[0], v[1]);
-              o[2 * i + 1] = pack_bf16(v[2], v[3]);
-            }
-          }
-          if (half == 0) {
-            // the previous TMA store of this warp must have finished reading the staging tile
-            if (lane == 0) tc::tma_store_wait_read();
-            __syncwarp();
-          }
-          // 128B-swizzled row: 16-byte chunk j of row r lives at chunk (j ^ (r & 7))
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t chunk = (uint32_t)((half * 4 + j) ^ (lane & 7));
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + chunk * 16u), "r"(o[4 * j]),
-                         "r"(o[4 * j + 1]), "r"(o[4 * j + 2]), "r"(o[4 * j + 3]) : "memory");
+            for (int i = 0; i < 4; ++i) rv_next[i] = row_ok ? __ldg(res_row + (c + 32) / 8 + i) : make_uint4(0, 0, 0, 0);
           }
         }
-        tc::fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          tc::tma_store_2d(&tmap_out, stage_buf, col0 + g, row0 + quarter * 32);
-          tc::tma_store_commit();
+        uint32_t o[16];
+        if (EPI == EPI_RES) {
+          const uint32_t* rw = reinterpret_cast<const uint32_t*>(rv);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 ga = *reinterpret_cast<const float4*>(tab0 + c + 4 * i);
+            const float4 cd = *reinterpret_cast<const float4*>(tab1 + c + 4 * i);
+            const float g4[4] = {ga.x, ga.y, ga.z, ga.w};
+            const float d4[4] = {cd.x, cd.y, cd.z, cd.w};
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int e = 4 * i + j;
+              const uint32_t w = rw[e >> 1];
+              const float res_raw = (e & 1) ? __uint_as_float(w & 0xffff0000u) : __uint_as_float(w << 16);
+              const float a = g4[j] * rstd;
+              v[j] = fmaf(res_raw - mu, a, __uint_as_float(r[e]) + d4[j]);
+              s_sum += v[j];
+              s_sq = fmaf(v[j], v[j], s_sq);
+            }
+            o[2 * i] = pack_bf16(v[0], v[1]);
+            o[2 * i + 1] = pack_bf16(v[2], v[3]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 cc = *reinterpret_cast<const float4*>(tab0 + c + 4 * i);
+            const float4 cd = *reinterpret_cast<const float4*>(tab1 + c + 4 * i);
+            const float c4[4] = {cc.x, cc.y, cc.z, cc.w};
+            const float d4[4] = {cd.x, cd.y, cd.z, cd.w};
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              v[j] = fmaf(rstd, fmaf(-mu, c4[j], __uint_as_float(r[4 * i + j])), d4[j]);
+              if (EPI == EPI_LNIN_GELU) v[j] = gelu_fast(v[j]);
+            }
+            o[2 * i] = pack_bf16(v[0], v[1]);
+            o[2 * i + 1] = pack_bf16(v[2], v[3]);
+          }
+        }
+        if (half == 0) {
+          // the TMA store that last read this staging buffer must be done with it
+          if (lane == 0) {
+            if (STAGE_BUFS == 2) tc::tma_store_wait_read_1();
+            else tc::tma_store_wait_read();
+          }
+          __syncwarp();
+        }
+        // 128B-swizzled row: 16-byte chunk j of row r lives at chunk (j ^ (r & 7))
+        const uint32_t srow = stage_row + (uint32_t)(sbuf * STAGING_BYTES);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t chunk = (uint32_t)((half * 4 + j) ^ (lane & 7));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + chunk * 16u), "r"(o[4 * j]),
+                       "r"(o[4 * j + 1]), "r"(o[4 * j + 2]), "r"(o[4 * j + 3]) : "memory");
+        }
+        if (half == 1) {
+          tc::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tc::tma_store_2d(&tmap_out, stage_buf + (size_t)sbuf * STAGING_BYTES, col0 + c - 32, row0 + quarter * 32);
+            tc::tma_store_commit();
+          }
+          if (STAGE_BUFS == 2) sbuf ^= 1;
+        }
+        if (ch + 1 < N_CHUNKS) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = r_next[i];
+          if (EPI == EPI_RES) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rv[i] = rv_next[i];
+          }
         }
       }
       // all TMEM reads of this warp are complete -> hand the accumulator back to the MMA warp
@@ -341,6 +422,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         else tc::mbar_arrive(&tmem_empty_bar[acc]);
       }
       if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      par ^= 1;
 
       if (EPI == EPI_RES) {
         if (COL_GROUPS == 1) {
@@ -359,7 +441,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
             p.out_stats[(size_t)row * STATS_PARTS + n_blk] = make_float2(s_sum, s_sq);
           }
-          asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
         }
       }
     }
