@@ -32,8 +32,11 @@ constexpr int QKV_TILE_BYTES = TILE * HEAD_DIM * 2;   // 8 KB: [128][32] bf16, 6
 constexpr int P_BYTES = 2 * TILE * 64 * 2;   // 32 KB per softmax group: two [128][64] bf16 k-blocks
 constexpr int GROUPS = 2;
 constexpr int THREADS = 32 * (4 * GROUPS + 2);
-constexpr int TMEM_COLS = 512;               // S0 [0,128)  S1 [128,256)  PV0 [256,288)  PV1 [288,320)
+constexpr int TMEM_COLS = 512;               // S0 [0,128)  S1 [128,256)  group g: PV [256+64g, +32)  L [+32, +48)
 constexpr int PV_COL = 256;
+constexpr int PV_STRIDE = 64;
+constexpr int L_OFF = 32;                    // L = P . 1: the softmax denominator comes out of the tensor core
+constexpr int ONES_BYTES = 2048;             // [16 rows][64] bf16 ones: the B operand of L (any swizzle: all equal)
 
 __host__ __device__ inline int item_stages(int max_len) {
   const int tiles = (max_len + TILE - 1) / TILE;
@@ -41,7 +44,7 @@ __host__ __device__ inline int item_stages(int max_len) {
 }
 __host__ __device__ inline size_t smem_bytes(int max_len) {
   const int tiles = (max_len + TILE - 1) / TILE;
-  return (size_t)item_stages(max_len) * 3 * tiles * QKV_TILE_BYTES + (size_t)GROUPS * P_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;
+  return (size_t)item_stages(max_len) * 3 * tiles * QKV_TILE_BYTES + (size_t)GROUPS * P_BYTES + ONES_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;
 }
 
 // K-major operand, rows of 64 bytes (32 bf16) under the 64-byte swizzle: 8-row groups 512 B apart
@@ -77,6 +80,12 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -97,7 +106,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16*
   const int hidden = heads * HEAD_DIM;
   const size_t stage_bytes = (size_t)3 * max_tiles * QKV_TILE_BYTES;  // [Q tiles | K tiles | V tiles]
   uint8_t* p_smem = smem + (size_t)n_stages * stage_bytes;            // multiple of 8 KB: 1024-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + (size_t)GROUPS * P_BYTES);
+  uint8_t* ones_smem = p_smem + (size_t)GROUPS * P_BYTES;            // 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones_smem + ONES_BYTES);
   uint64_t* kv_full = bars;          // [2]  TMA -> MMA
   uint64_t* kv_empty = bars + 2;     // [2]  MMA -> TMA (all MMAs of the item retired)
   uint64_t* s_full = bars + 4;       // [GROUPS] MMA -> softmax: S complete
@@ -129,6 +139,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16*
     tc::tmem_alloc(tmem_ptr_smem, TMEM_COLS);
     tc::tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < ONES_BYTES / 4; i += THREADS) reinterpret_cast<uint32_t*>(ones_smem)[i] = 0x3f803f80u;
+  tc::fence_proxy_async();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -162,6 +174,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16*
     if (lane == 0) {
       constexpr uint32_t idesc_s = idesc_bf16(TILE, TILE, false);
       constexpr uint32_t idesc_o = idesc_bf16(TILE, HEAD_DIM, true);
+      constexpr uint32_t idesc_l = idesc_bf16(TILE, 16, false);
+      const uint64_t ones_desc = tc::umma_desc_sw128(tc::smem_u32(ones_smem));
       int stage = 0;
       uint32_t phase = 0;
       uint32_t p_waits[GROUPS] = {0, 0};  // completed waits on p_full[g]
@@ -193,7 +207,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16*
               for (int j = 0; j < TILE / 16; ++j) {
                 const uint64_t a_desc = tc::umma_desc_sw128(p_addr + (uint32_t)((j >> 2) * (TILE * 128))) + (uint64_t)((j & 3) * 2);
                 const uint64_t b_desc = desc_mn_sw64(v_addr + (uint32_t)(j * 16 * 64));
-                tc::umma_bf16(tmem_base + PV_COL + g * HEAD_DIM, a_desc, b_desc, idesc_o, j != 0 ? 1u : 0u);
+                tc::umma_bf16(tmem_base + PV_COL + g * PV_STRIDE, a_desc, b_desc, idesc_o, j != 0 ? 1u : 0u);
+                tc::umma_bf16(tmem_base + PV_COL + g * PV_STRIDE + L_OFF, a_desc, ones_desc, idesc_l, j != 0 ? 1u : 0u);
               }
               tc::umma_commit(&o_full[g]);
             }
@@ -220,7 +235,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16*
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t s_tmem = lane_base + g * TILE;
-    const uint32_t pv_tmem = lane_base + PV_COL + g * HEAD_DIM;
+    const uint32_t pv_tmem = lane_base + PV_COL + g * PV_STRIDE;
     const uint32_t p_row = tc::smem_u32(p_smem + (size_t)g * P_BYTES) + (uint32_t)row * 128u;
     uint32_t n_s = 0, n_o = 0;  // completed waits on s_full[g] / o_full[g]
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -238,19 +253,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16*
           tc::mbar_wait(&s_full[g], n_s & 1);
           ++n_s;
           tc::tc_fence_after();
-          uint32_t r[TILE];
-#pragma unroll
-          for (int c = 0; c < TILE / 32; ++c) tc::tmem_ld32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
-          tc::tmem_ld_wait();
+          // pass 1: row maximum.  S is read from TMEM twice (32 columns at a time, the next load in
+          // flight during the current chunk) instead of holding 128 scores in registers.
           float mx = -INFINITY;
-          if (n_keys >= TILE) {
+          {
+            uint32_t ra[32], rb[32];
+            tc::tmem_ld32(s_tmem, ra);
 #pragma unroll
-            for (int i = 0; i < TILE; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-          } else {
+            for (int c = 0; c < TILE / 32; ++c) {
+              tc::tmem_ld_wait();
+              uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+              uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
+              if (c + 1 < TILE / 32) tc::tmem_ld32(s_tmem + (c + 1) * 32, nxt);
+              if (n_keys < (c + 1) * 32) {
 #pragma unroll
-            for (int i = 0; i < TILE; ++i) {
-              if (i >= n_keys) r[i] = 0xff800000u;  // -inf: p = 0
-              mx = fmaxf(mx, __uint_as_float(r[i]));
+                for (int i = 0; i < 32; ++i)
+                  if (c * 32 + i >= n_keys) cur[i] = 0xff800000u;
+              }
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(cur[i]), __uint_as_float(cur[i + 1]));
             }
           }
           const float m_new = fmaxf(m, mx);
@@ -264,34 +285,44 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16*
             tc::tc_fence_after();
             uint32_t pv[HEAD_DIM];
             tc::tmem_ld32(pv_tmem, pv);
+            const uint32_t lv = tc::tmem_ld1(pv_tmem + L_OFF);
             tc::tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < HEAD_DIM; ++i) o[i] = (o[i] + __uint_as_float(pv[i])) * alpha;
+            l = (l + __uint_as_float(lv)) * alpha;
           }
-          // exponentials, row sum (of the bf16-rounded weights the tensor core will use), P -> smem
-          float sum = 0.f;
+          // exponentials; P -> bf16 -> smem.  The row sum is NOT taken here: L = P . 1 comes out of the
+          // tensor core next to P V, over exactly the bf16 weights the numerator uses.
+          {
+            uint32_t ra[32], rb[32];
+            tc::tmem_ld32(s_tmem, ra);
 #pragma unroll
-          for (int c0 = 0; c0 < TILE; c0 += 32) {
-            uint32_t pk[16];
+            for (int c = 0; c < TILE / 32; ++c) {
+              const int c0 = c * 32;
+              tc::tmem_ld_wait();
+              uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+              uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
+              if (c + 1 < TILE / 32) tc::tmem_ld32(s_tmem + (c + 1) * 32, nxt);
+              uint32_t pk[16];
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float p0 = ex2(fmaf(__uint_as_float(r[c0 + i]), scale_log2, -off));
-              const float p1 = ex2(fmaf(__uint_as_float(r[c0 + i + 1]), scale_log2, -off));
-              const uint32_t w = pack2(p0, p1);
-              pk[i >> 1] = w;
-              sum += __uint_as_float(w << 16) + __uint_as_float(w & 0xffff0000u);
-            }
-            // k-block (c0 / 64) of P; 16-byte chunk j of row r lives at chunk (j ^ (r & 7))
-            const uint32_t blk = p_row + (uint32_t)((c0 >> 6) * (TILE * 128));
-            const int chunk0 = (c0 & 32) >> 3;
+              for (int i = 0; i < 32; i += 2) {
+                float p0 = ex2(fmaf(__uint_as_float(cur[i]), scale_log2, -off));
+                float p1 = ex2(fmaf(__uint_as_float(cur[i + 1]), scale_log2, -off));
+                if (c0 + i >= n_keys) p0 = 0.f;       // keys beyond the sequence (last block only)
+                if (c0 + i + 1 >= n_keys) p1 = 0.f;
+                pk[i >> 1] = pack2(p0, p1);
+              }
+              // k-block (c0 / 64) of P; 16-byte chunk j of row r lives at chunk (j ^ (r & 7))
+              const uint32_t blk = p_row + (uint32_t)((c0 >> 6) * (TILE * 128));
+              const int chunk0 = (c0 & 32) >> 3;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t chunk = (uint32_t)((chunk0 + j) ^ (row & 7));
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + chunk * 16u), "r"(pk[4 * j]),
-                           "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t chunk = (uint32_t)((chunk0 + j) ^ (row & 7));
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + chunk * 16u), "r"(pk[4 * j]),
+                             "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
+              }
             }
           }
-          l = l * alpha + sum;
           tc::fence_proxy_async();   // P (generic-proxy stores) -> visible to the tensor core
           tc::tc_fence_before();
           __syncwarp();
@@ -303,11 +334,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16*
         tc::tc_fence_after();
         uint32_t pv[HEAD_DIM];
         tc::tmem_ld32(pv_tmem, pv);
+        const uint32_t lv = tc::tmem_ld1(pv_tmem + L_OFF);
         tc::tmem_ld_wait();
         tc::tc_fence_before();
         const int qrow = qt * TILE + row;
         if (qrow < S) {
-          const float inv = 1.f / l;
+          const float inv = 1.f / (l + __uint_as_float(lv));
           uint4* dst = reinterpret_cast<uint4*>(ctx + (size_t)(tok0 + qrow) * hidden + head * HEAD_DIM);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
