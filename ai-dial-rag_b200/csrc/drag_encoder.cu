@@ -334,16 +334,19 @@ int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* q
     attn_tc::attention_tc_kernel<<<items < sms ? items : sms, attn_tc::THREADS, smem, st>>>(
         tm_qkv_heads, ctx, d_cu, n_seq, heads, (max_len + attn_tc::TILE - 1) / attn_tc::TILE, attn_tc::item_stages(max_len), scale_log2);
   } else {
-    const int s_pad = (max_len + 63) & ~63;
-    const size_t smem = (size_t)2 * s_pad * attn::KV_STRIDE * sizeof(bf16);
-    attn::attention_kernel<<<dim3(heads, n_seq), attn::WARPS * 32, smem, st>>>(qkv, ctx, d_cu, heads * HEAD_DIM, scale_log2);
+    const size_t smem = attn::smem_bytes(max_len);
+    const int q_tiles = (max_len + attn::ROWS_PER_CTA - 1) / attn::ROWS_PER_CTA;
+    for (int s0 = 0; s0 < n_seq; s0 += 65535) {   // gridDim.y limit
+      const int n = n_seq - s0 < 65535 ? n_seq - s0 : 65535;
+      attn::attention_kernel<<<dim3(heads * q_tiles, n), attn::WARPS * 32, smem, st>>>(qkv, ctx, d_cu + s0, heads, scale_log2);
+    }
   }
   DRAG_CUDA_OK(cudaGetLastError());
   return DRAG_OK;
 }
 
 int attention_set_attributes() {
-  DRAG_CUDA_OK(cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 512 * attn::KV_STRIDE * 2));
+  DRAG_CUDA_OK(cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::smem_bytes(512)));
   DRAG_CUDA_OK(cudaFuncSetAttribute(attn_tc::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_tc::smem_bytes(512)));
   return DRAG_OK;
 }
