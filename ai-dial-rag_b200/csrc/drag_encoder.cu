@@ -12,6 +12,7 @@
 //               are stored raw (pre-LN, bf16) with per-row (sum, sum^2) partials.
 // All GEMMs are the tcgen05/TMA kernel of drag_gemm.cuh with fused epilogues.
 #include <stdlib.h>
+#include <cuda_fp16.h>
 
 #include <mutex>
 #include <new>
@@ -31,6 +32,7 @@ constexpr int HIDDEN = 384;
 constexpr int HEAD_DIM = 32;
 constexpr int QKV_BLOCK_N = 192;   // 1152 = 6 x 192
 constexpr int FFN_BLOCK_N = 256;   // 1536 = 6 x 256
+constexpr int FFN_BLOCK_N_PAIR = 256;  // CTA-pair FFN-up (a weights-stationary 192-column form measured slower inside the step: 0.389 vs 0.340 ms)
 constexpr int RES_BLOCK_N = 128;   // 384 = 3 x 128 (one statistics slot per tile)
 constexpr int RES_BLOCK_N_PAIR = 192;  // CTA-pair kernels: 384 = 2 x 192 (third statistics slot stays zero)
 constexpr int PARTS = gemm::STATS_PARTS;
@@ -274,17 +276,31 @@ int upload_bf16(drag_encoder* e, bf16** dst, std::initializer_list<const float*>
   return DRAG_OK;
 }
 
+// [rows, cols] fp32 host matrix as an fp16 device matrix (the FFN-down weights: their A operand is the fp16 GELU output)
+int upload_f16(drag_encoder* e, bf16** dst, const float* src, size_t rows, size_t cols) {
+  std::vector<__half> tmp(rows * cols);
+  for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = __float2half_rn(src[i]);
+  int rc = dev_alloc(e, dst, tmp.size());
+  if (rc) return rc;
+  DRAG_CUDA_OK(cudaMemcpy(*dst, tmp.data(), tmp.size() * 2, cudaMemcpyHostToDevice));
+  return DRAG_OK;
+}
+
 int upload_concat_f32(drag_encoder* e, float** dst, std::initializer_list<const float*> srcs, size_t n_each) {
   std::vector<float> tmp;
   for (const float* s : srcs) tmp.insert(tmp.end(), s, s + n_each);
   return upload_f32(e, dst, tmp.data(), tmp.size());
 }
 
-template <int BLOCK_N, int EPI, int EPI_WARPS, int STAGES, int CG>
+template <int BLOCK_N, int EPI, int EPI_WARPS, int STAGES, int CG, bool WS = false>
 int launch_gemm(const drag_encoder* e, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tout,
                 const gemm::GemmParams& p, cudaStream_t st) {
-  auto kern = gemm::gemm_kernel<BLOCK_N, EPI, EPI_WARPS, STAGES, CG>;
-  constexpr size_t smem = gemm::smem_bytes<BLOCK_N, STAGES, EPI_WARPS, CG>();
+  auto kern = gemm::gemm_kernel<BLOCK_N, EPI, EPI_WARPS, STAGES, CG, WS>;
+  constexpr size_t smem = gemm::smem_bytes<BLOCK_N, STAGES, EPI_WARPS, CG, WS>();
+  if (WS) {
+    DRAG_REQUIRE(p.K <= gemm::WS_K_BLOCKS * gemm::BLOCK_K, "weights-stationary GEMM holds at most K=%d (got %d)", gemm::WS_K_BLOCKS * gemm::BLOCK_K, p.K);
+    DRAG_REQUIRE(e->sms / CG >= p.N / BLOCK_N, "weights-stationary GEMM needs at least one worker per column block");
+  }
   static_assert(smem <= 227 * 1024, "GEMM configuration exceeds the 227 KB shared memory of an SM");
   static std::once_flag once[16];
   static cudaError_t attr_err[16];
@@ -356,9 +372,11 @@ int attention_set_attributes() {
 #define DRAG_GEMM_UP   launch_gemm<FFN_BLOCK_N, gemm::EPI_LNIN_GELU, 8, 3, 1>
 #define DRAG_GEMM_RES  launch_gemm<RES_BLOCK_N, gemm::EPI_RES, 8, 5, 1>
 // ... and their CTA-pair (cta_group::2) forms: 256 x BLOCK_N tiles, half a W tile per CTA
-#define DRAG_GEMM2_QKV launch_gemm<QKV_BLOCK_N, gemm::EPI_LNIN, 4, 6, 2>
-#define DRAG_GEMM2_UP  launch_gemm<FFN_BLOCK_N, gemm::EPI_LNIN_GELU, 8, 4, 2>
+// (the K = 384 ones keep their W column block resident in shared memory: "weights stationary")
+#define DRAG_GEMM2_QKV launch_gemm<QKV_BLOCK_N, gemm::EPI_LNIN, 4, 6, 2, true>
+#define DRAG_GEMM2_UP  launch_gemm<FFN_BLOCK_N_PAIR, gemm::EPI_LNIN_GELU, 8, 4, 2>
 #define DRAG_GEMM2_RES launch_gemm<RES_BLOCK_N_PAIR, gemm::EPI_RES, 12, 6, 2>
+#define DRAG_GEMM2_RES_WS launch_gemm<RES_BLOCK_N_PAIR, gemm::EPI_RES, 12, 6, 2, true>
 
 int forward_impl(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu, const int32_t* h_cu, int n_seq,
                  float* d_out, int stop_after_layer, float* d_hidden, cudaStream_t st) {
@@ -411,7 +429,7 @@ int forward_impl(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu, con
     p.residual = e->x; p.out_stats = e->stats_y;
     {
       ProfScope prof(e, KC_GEMM_OUT_LN, st);
-      rc = (e->gemm_pairs & 2) ? DRAG_GEMM2_RES(e, e->tm_ctx, L.tp_o, e->ts_y, p, st) : DRAG_GEMM_RES(e, e->tm_ctx, L.tm_o, e->ts_y, p, st);
+      rc = (e->gemm_pairs & 2) ? DRAG_GEMM2_RES_WS(e, e->tm_ctx, L.tp_o, e->ts_y, p, st) : DRAG_GEMM_RES(e, e->tm_ctx, L.tm_o, e->ts_y, p, st);
     }
     if (rc) return rc;
     // h = gelu(LN_1(y) . W1^T + b_1)
@@ -424,7 +442,7 @@ int forward_impl(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu, con
     if (rc) return rc;
     // x_raw = h . W2^T + b_2 + LN_1(y_raw)   (+ row statistics of x_raw); LN_2 is applied by the consumers
     p.N = HIDDEN; p.K = sh.inter; p.colc = nullptr; p.cold = L.down_cold; p.gamma = L.down_gamma; p.in_stats = e->stats_y;
-    p.residual = e->y; p.out_stats = e->stats_x;
+    p.residual = e->y; p.out_stats = e->stats_x; p.f16_operands = 1;   // h and W2 are fp16
     {
       ProfScope prof(e, KC_GEMM_DOWN_LN, st);
       rc = (e->gemm_pairs & 8) ? DRAG_GEMM2_RES(e, e->tm_h, L.tp_down, e->ts_x, p, st) : DRAG_GEMM_RES(e, e->tm_h, L.tm_down, e->ts_x, p, st);
@@ -495,7 +513,7 @@ extern "C" int drag_encoder_create(const drag_bert_shape* shape, const float* co
   *out = nullptr;
   DRAG_REQUIRE(shape->hidden == HIDDEN, "drag_encoder_create: this build supports hidden=384 (got %d)", shape->hidden);
   DRAG_REQUIRE(shape->heads * HEAD_DIM == shape->hidden, "drag_encoder_create: head_dim must be 32");
-  DRAG_REQUIRE(shape->inter % FFN_BLOCK_N == 0 && shape->inter % gemm::BLOCK_K == 0, "drag_encoder_create: intermediate size must be a multiple of 256");
+  DRAG_REQUIRE(shape->inter % FFN_BLOCK_N == 0 && shape->inter % FFN_BLOCK_N_PAIR == 0 && shape->inter % gemm::BLOCK_K == 0, "drag_encoder_create: intermediate size must be a multiple of 256");
   static_assert(HIDDEN / RES_BLOCK_N == PARTS, "one statistics slot per residual-GEMM column tile");
   DRAG_REQUIRE(shape->layers >= 1 && shape->vocab >= 1 && shape->max_pos >= 1 && shape->max_pos <= 512, "drag_encoder_create: bad shape");
   DRAG_REQUIRE(n_tensors == 5 + 16 * shape->layers, "drag_encoder_create: expected %d tensors, got %d", 5 + 16 * shape->layers, n_tensors);
@@ -536,7 +554,7 @@ extern "C" int drag_encoder_create(const drag_bert_shape* shape, const float* co
     if ((rc = upload_sum_f32(e, &L.o_cold, t[7], b_in, H))) return bail(rc);
     if ((rc = upload_f32(e, &L.o_gamma, g_in, H))) return bail(rc);
     if ((rc = upload_folded(e, &L.w_up, &L.up_c, &L.up_d, {t[8]}, {t[9]}, F, H, g_1, b_1))) return bail(rc);
-    if ((rc = upload_bf16(e, &L.w_down, {t[10]}, H, F))) return bail(rc);
+    if ((rc = upload_f16(e, &L.w_down, t[10], H, F))) return bail(rc);
     if ((rc = upload_sum_f32(e, &L.down_cold, t[11], b_1, H))) return bail(rc);
     if ((rc = upload_f32(e, &L.down_gamma, g_1, H))) return bail(rc);
     if ((rc = upload_f32(e, &L.ln2_g, t[14], H))) return bail(rc);
@@ -547,7 +565,7 @@ extern "C" int drag_encoder_create(const drag_bert_shape* shape, const float* co
     if ((rc = make_tmap(&L.tm_down, L.w_down, H, F, RES_BLOCK_N))) return bail(rc);
     if ((rc = make_tmap(&L.tp_qkv, L.w_qkv, 3 * H, H, QKV_BLOCK_N / 2))) return bail(rc);
     if ((rc = make_tmap(&L.tp_o, L.w_o, H, H, RES_BLOCK_N_PAIR / 2))) return bail(rc);
-    if ((rc = make_tmap(&L.tp_up, L.w_up, F, H, FFN_BLOCK_N / 2))) return bail(rc);
+    if ((rc = make_tmap(&L.tp_up, L.w_up, F, H, FFN_BLOCK_N_PAIR / 2))) return bail(rc);
     if ((rc = make_tmap(&L.tp_down, L.w_down, H, F, RES_BLOCK_N_PAIR / 2))) return bail(rc);
   }
   const size_t T = (size_t)e->max_tokens;
@@ -685,6 +703,8 @@ extern "C" int drag_debug_gemm(int device, int variant, const void* d_a, const v
   if (rc) return rc;
   if ((rc = make_tmap(&tout, d_out, (uint64_t)M, (uint64_t)N, gemm::STORE_ROWS))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (const char* dbg = getenv("DRAG_GEMM_DBG")) p.dbg = atoi(dbg);
+  if (variant >= 20) { p.f16_operands = 1; variant -= 20; }   // A and W hold fp16
   switch (variant) {
     case 0:
       DRAG_REQUIRE(N % QKV_BLOCK_N == 0 && d_colc, "drag_debug_gemm: variant 0 needs N %% %d == 0 and colc", QKV_BLOCK_N);
@@ -703,13 +723,13 @@ extern "C" int drag_debug_gemm(int device, int variant, const void* d_a, const v
       if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, QKV_BLOCK_N / 2))) return rc;
       return DRAG_GEMM2_QKV(&fake, ta, tw, tout, p, st);
     case 11:
-      DRAG_REQUIRE(N % FFN_BLOCK_N == 0 && d_colc, "drag_debug_gemm: variant 11 needs N %% %d == 0 and colc", FFN_BLOCK_N);
-      if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, FFN_BLOCK_N / 2))) return rc;
+      DRAG_REQUIRE(N % FFN_BLOCK_N_PAIR == 0 && d_colc, "drag_debug_gemm: variant 11 needs N %% %d == 0 and colc", FFN_BLOCK_N_PAIR);
+      if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, FFN_BLOCK_N_PAIR / 2))) return rc;
       return DRAG_GEMM2_UP(&fake, ta, tw, tout, p, st);
     case 12:
       DRAG_REQUIRE(N == HIDDEN && d_gamma && d_residual && d_out_stats, "drag_debug_gemm: variant 12 needs N=384, gamma, residual, out_stats");
       if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, RES_BLOCK_N_PAIR / 2))) return rc;
-      return DRAG_GEMM2_RES(&fake, ta, tw, tout, p, st);
+      return K <= gemm::WS_K_BLOCKS * gemm::BLOCK_K ? DRAG_GEMM2_RES_WS(&fake, ta, tw, tout, p, st) : DRAG_GEMM2_RES(&fake, ta, tw, tout, p, st);
     default:
       return fail(DRAG_ERR_INVALID, "drag_debug_gemm: unknown variant %d", variant);
   }

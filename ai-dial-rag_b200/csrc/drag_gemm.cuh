@@ -13,7 +13,7 @@
 // i.e. the tensor cores multiply the raw rows by gamma-scaled weights and the epilogue applies
 // the per-row (mu, rstd) and per-column (c, d) terms.  Epilogues:
 //     EPI_LNIN       out = rstd*(acc - mu*c) + d                               (QKV projection)
-//     EPI_LNIN_GELU  out = gelu(rstd*(acc - mu*c) + d)                         (FFN up)
+//     EPI_LNIN_GELU  out = gelu(rstd*(acc - mu*c) + d)   stored as FP16            (FFN up)
 //     EPI_RES        out = acc + cold + LN(residual_raw)  (raw, pre-LN) and the row's partial
 //                    (sum, sum^2) over this tile's columns -> out_stats   (attention out / FFN down)
 //
@@ -21,6 +21,11 @@
 // each CTA stages its own 128 rows of A and HALF of the W tile (BLOCK_N/2 rows), the leader issues
 // M=256 MMAs that read both halves, and each CTA drains its own 128 accumulator rows.  Operand bytes
 // per flop drop by a third or more, which is what bounds the K=384 GEMMs (L2 -> SM traffic).
+//
+// WS = true ("weights stationary", the K = 384 GEMMs): the L2 -> SM fabric (~6300 B/clk chip-wide) is what
+// bounds these GEMMs -- a 256 x 192 pair tile moves 336 KB of operands and 96 KB of output for 2304 MMA
+// clocks.  A worker therefore keeps ONE column block of W (all of K) resident in shared memory for the
+// whole kernel and walks down the rows: only A streams through the ring (-33..37% fabric bytes).
 //
 // CTA = 2 + EPI_WARPS warps, one CTA per SM, looping over 128 x BLOCK_N output tiles:
 //   warp 0   TMA producer (cp.async.bulk.tensor, 128B swizzle) into a STAGES-deep smem ring
@@ -59,6 +64,8 @@ struct GemmParams {
   float ln_eps;
   const __nv_bfloat16* residual;   // [M, N] raw residual rows (RES)
   float2* out_stats;               // [M][STATS_PARTS] (RES): slot n_blk of every row
+  int f16_operands;                // A and W hold fp16 (the FFN-down GEMM: GELU writes fp16), else bf16
+  int dbg;                         // ablation switches for the probes (DRAG_GEMM_DBG): 1 no output stores, 2 no epilogue work at all, 4 all stores land on the first row block (L2-resident)
 };
 
 template <int BLOCK_N>
@@ -75,23 +82,49 @@ struct Cfg {
 template <int BLOCK_N, int EPI_WARPS>
 constexpr int stage_bufs() { return (BLOCK_N / (EPI_WARPS / 4)) > STORE_COLS ? 2 : 1; }
 
-template <int BLOCK_N, int STAGES, int EPI_WARPS, int CG = 1>
+constexpr int WS_K_BLOCKS = 6;   // weights-stationary kernels hold K = 384 (6 k-blocks) of their W column block
+
+template <int BLOCK_N, int STAGES, int EPI_WARPS, int CG = 1, bool WS = false>
 constexpr size_t smem_bytes() {
-  // ring + per-warp store staging + [barriers, tmem pointer, statistics exchange | 4 KB] + [column constants:
-  // 2 tiles x 2 vectors x BLOCK_N floats <= 4 KB] + slack for manual 1024-byte alignment
-  return (size_t)STAGES * (A_STAGE_BYTES + Cfg<BLOCK_N>::B_STAGE_BYTES / CG) +
+  // ring (A + W, or A only next to the resident W block) + per-warp store staging + [barriers, tmem pointer,
+  // statistics exchange | 4 KB] + [column constants: 2 tiles x 2 vectors x BLOCK_N floats <= 4 KB] + slack for
+  // manual 1024-byte alignment
+  return (WS ? (size_t)STAGES * A_STAGE_BYTES + (size_t)WS_K_BLOCKS * (Cfg<BLOCK_N>::B_STAGE_BYTES / CG)
+             : (size_t)STAGES * (A_STAGE_BYTES + Cfg<BLOCK_N>::B_STAGE_BYTES / CG)) +
          (size_t)EPI_WARPS * stage_bufs<BLOCK_N, EPI_WARPS>() * STAGING_BYTES + 8192 + 1024;
 }
 
+// Packed fp32 pairs (FFMA2: one instruction per two lanes of the epilogue arithmetic)
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 // GELU(x) = x * Phi(x) with Phi(x) ~ 0.5 * (1 + tanh(x * (c0 + c1 x^2 + c2 x^4))): minimax fit on
-// [-8, 8] (max abs error 2.5e-5 vs the erf form, far below the bf16 output rounding); one MUFU.TANH.
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float x2 = fminf(x * x, 64.0f);
-  const float p = fmaf(fmaf(-0.00035152308f, x2, 0.03700567580f), x2, 0.79750785923f);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * p));
-  const float hx = 0.5f * x;
-  return fmaf(hx, t, hx);
+// [-8, 8] (max abs error 2.5e-5 vs the erf form).  Evaluated on PAIRS in fp16 (HFMA2 / MUFU.TANH.F16):
+// half the instructions of the fp32 form; the result is stored as fp16 (11-bit significand, finer than
+// the bf16 the other activations use), which the FFN-down GEMM reads as its A operand.
+__device__ __forceinline__ uint32_t gelu_f16x2(float x_lo, float x_hi) {
+  uint32_t x, x2, p, t, hx, o;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(x) : "f"(x_hi), "f"(x_lo));
+  asm("mul.rn.f16x2 %0, %1, %1;" : "=r"(x2) : "r"(x));
+  asm("min.f16x2 %0, %1, %2;" : "=r"(x2) : "r"(x2), "r"(0x54005400u));                      // min(x^2, 64)
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(p) : "r"(0x8dc28dc2u), "r"(x2), "r"(0x28bd28bdu));  // -0.00035152 x2 + 0.0370057
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(p) : "r"(p), "r"(x2), "r"(0x3a613a61u));          // ... x2 + 0.7975079
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(p) : "r"(x), "r"(p));
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(p));
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(hx) : "r"(x), "r"(0x38003800u));                       // 0.5 x
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(o) : "r"(hx), "r"(t), "r"(hx));
+  return o;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -114,14 +147,15 @@ __device__ __forceinline__ void row_stats(const float2* stats, int row, bool ok,
   rstd = rsqrtf(fmaxf(ss * inv_width - mu * mu, 0.f) + eps);
 }
 
-template <int BLOCK_N, int EPI, int EPI_WARPS, int STAGES, int CG>
+template <int BLOCK_N, int EPI, int EPI_WARPS, int STAGES, int CG, bool WS>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
             const __grid_constant__ CUtensorMap tmap_out, GemmParams p) {
   using C = Cfg<BLOCK_N>;
   static_assert(CG == 1 || CG == 2, "single CTAs or CTA pairs");
-  constexpr int B_BYTES = C::B_STAGE_BYTES / CG;          // this CTA's part of the W tile
-  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_BYTES;
+  constexpr int B_BYTES = C::B_STAGE_BYTES / CG;          // this CTA's part of the W tile (one k-block)
+  constexpr int STAGE_BYTES = WS ? A_STAGE_BYTES : A_STAGE_BYTES + B_BYTES;
+  constexpr int W_RESIDENT_BYTES = WS ? WS_K_BLOCKS * B_BYTES : 0;
   constexpr int TILE_M = BLOCK_M * CG;
   static_assert(EPI_WARPS % 4 == 0 && EPI_WARPS >= 4 && EPI_WARPS <= 16, "epilogue warps come in groups of 4 (one per TMEM lane quarter)");
   static_assert(EPI != EPI_RES || EPI_WARPS <= 12, "the statistics exchange of EPI_RES handles at most three column groups");
@@ -132,13 +166,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* ring = smem;
-  uint8_t* staging = smem + (size_t)STAGES * STAGE_BYTES;  // 1024-aligned, 4 KB per epilogue warp
+  uint8_t* w_res = smem;                                   // WS: [k_blocks][this CTA's W rows][64] resident
+  uint8_t* ring = smem + W_RESIDENT_BYTES;
+  uint8_t* staging = ring + (size_t)STAGES * STAGE_BYTES;  // 1024-aligned, 4 KB per epilogue warp
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + (size_t)EPI_WARPS * STAGE_BUFS * STAGING_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* w_bar = tmem_empty_bar + 2;                    // WS: the resident W block has landed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -149,6 +185,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const uint32_t cta_rank = CG == 2 ? tc::cluster_ctarank() : 0u;   // 0 = pair leader
   const int worker = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int n_workers = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // The worker's tile walk.  Default: tiles worker, worker + n_workers, ... in row-major tile order.
+  // WS: workers are dealt to column blocks (worker % n_tiles) and walk down the rows with the
+  // other workers of their column block; workers beyond a whole number of groups stay idle.
+  const int ws_groups = n_workers / n_tiles;
+  const int ws_n_blk = worker % n_tiles, ws_g = worker / n_tiles;
+  const int my_tiles = WS ? ((ws_g < ws_groups && ws_g < m_tiles) ? (m_tiles - ws_g + ws_groups - 1) / ws_groups : 0)
+                          : (worker < num_tiles ? (num_tiles - worker + n_workers - 1) / n_workers : 0);
+  auto tile_m = [&](int it) { return WS ? ws_g + it * ws_groups : (worker + it * n_workers) / n_tiles; };
+  auto tile_n = [&](int it) { return WS ? ws_n_blk : (worker + it * n_workers) % n_tiles; };
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmap_a);
@@ -162,6 +207,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       tc::mbar_init(&tmem_full_bar[s], 1);
       tc::mbar_init(&tmem_empty_bar[s], CG * EPI_WARPS);   // the leader's collects both CTAs' epilogue warps
     }
+    tc::mbar_init(w_bar, 1);
     tc::fence_barrier_init();
   }
   if (CG == 2) tc::cluster_sync_all();   // the peer's barriers must exist before anything signals them
@@ -184,8 +230,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = worker; tile < num_tiles; tile += n_workers) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      if (WS && my_tiles > 0) {
+        // the worker's column block of W, all of K, once
+        if (CG == 2) {
+          if (cta_rank == 0) tc::mbar_arrive_expect_tx(w_bar, (uint32_t)(2 * k_blocks * B_BYTES));
+          const uint32_t bar = tc::mapa_shared(tc::smem_u32(w_bar), 0);
+          for (int kb = 0; kb < k_blocks; ++kb)
+            tc::tma_load_2d_pair(&tmap_w, bar, w_res + (size_t)kb * B_BYTES, kb * BLOCK_K, ws_n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / 2));
+        } else {
+          tc::mbar_arrive_expect_tx(w_bar, (uint32_t)(k_blocks * B_BYTES));
+          for (int kb = 0; kb < k_blocks; ++kb)
+            tc::tma_load_2d(&tmap_w, w_bar, w_res + (size_t)kb * B_BYTES, kb * BLOCK_K, ws_n_blk * BLOCK_N);
+        }
+      }
+      for (int it = 0; it < my_tiles; ++it) {
+        const int m_blk = tile_m(it), n_blk = tile_n(it);
         for (int kb = 0; kb < k_blocks; ++kb) {
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = ring + (size_t)stage * STAGE_BYTES;
@@ -194,11 +253,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             if (cta_rank == 0) tc::mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
             const uint32_t bar = tc::mapa_shared(tc::smem_u32(&full_bar[stage]), 0);
             tc::tma_load_2d_pair(&tmap_a, bar, a_dst, kb * BLOCK_K, m_blk * TILE_M + (int)cta_rank * BLOCK_M);
-            tc::tma_load_2d_pair(&tmap_w, bar, a_dst + A_STAGE_BYTES, kb * BLOCK_K, n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / 2));
+            if (!WS) tc::tma_load_2d_pair(&tmap_w, bar, a_dst + A_STAGE_BYTES, kb * BLOCK_K, n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / 2));
           } else {
             tc::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
             tc::tma_load_2d(&tmap_a, &full_bar[stage], a_dst, kb * BLOCK_K, m_blk * BLOCK_M);
-            tc::tma_load_2d(&tmap_w, &full_bar[stage], a_dst + A_STAGE_BYTES, kb * BLOCK_K, n_blk * BLOCK_N);
+            if (!WS) tc::tma_load_2d(&tmap_w, &full_bar[stage], a_dst + A_STAGE_BYTES, kb * BLOCK_K, n_blk * BLOCK_N);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -208,12 +267,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && cta_rank == 0) {
-      constexpr uint32_t idesc = tc::umma_idesc_bf16(TILE_M, BLOCK_N);
+      const uint32_t idesc = p.f16_operands ? tc::umma_idesc_f16(TILE_M, BLOCK_N) : tc::umma_idesc_bf16(TILE_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = worker; tile < num_tiles; tile += n_workers) {
+      if (WS && my_tiles > 0) {
+        tc::mbar_wait(w_bar, 0);
+        tc::tc_fence_after();
+      }
+      for (int it = 0; it < my_tiles; ++it) {
         tc::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -222,7 +285,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           tc::tc_fence_after();
           const uint32_t a_addr = tc::smem_u32(ring + (size_t)stage * STAGE_BYTES);
           const uint64_t a_desc = tc::umma_desc_sw128(a_addr);
-          const uint64_t b_desc = tc::umma_desc_sw128(a_addr + A_STAGE_BYTES);
+          const uint64_t b_desc = tc::umma_desc_sw128(WS ? tc::smem_u32(w_res + (size_t)kb * B_BYTES) : a_addr + A_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // +32 bytes per 16-element k-step inside the 128-byte swizzle row (encoded >> 4)
@@ -261,9 +324,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     int par = 0, sbuf = 0;
     const uint32_t leader_tmem_empty = CG == 2 ? tc::mapa_shared(tc::smem_u32(&tmem_empty_bar[0]), 0) : 0u;
 
-    auto fetch_cols = [&](int tile_, int par_) {
+    auto fetch_cols = [&](int it_, int par_) {
       // BLOCK_N/4 16-byte chunks of each of the two column vectors of the tile's column block
-      const int n_blk_ = tile_ % n_tiles;
+      const int n_blk_ = tile_n(it_);
       if (et < BLOCK_N / 2) {
         const bool second = et >= BLOCK_N / 4;
         const int chunk = second ? et - BLOCK_N / 4 : et;
@@ -273,8 +336,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto fetch_stats = [&](int tile_, float2 (&st)[STATS_PARTS]) {
-      const int row_ = (tile_ / n_tiles) * TILE_M + (int)cta_rank * BLOCK_M + row_in_tile;
+    auto fetch_stats = [&](int it_, float2 (&st)[STATS_PARTS]) {
+      const int row_ = tile_m(it_) * TILE_M + (int)cta_rank * BLOCK_M + row_in_tile;
       // volatile asm: the loads must be ISSUED here (a tile ahead of their use), not sunk to the use
 #pragma unroll
       for (int i = 0; i < STATS_PARTS; ++i) {
@@ -285,12 +348,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     };
 
     float2 next_stats[STATS_PARTS];
-    if (worker < num_tiles) {
-      fetch_cols(worker, 0);
-      fetch_stats(worker, next_stats);
+    if (my_tiles > 0) {
+      fetch_cols(0, 0);
+      fetch_stats(0, next_stats);
     }
-    for (int tile = worker; tile < num_tiles; tile += n_workers) {
-      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int m_blk = tile_m(it), n_blk = tile_n(it);
       const int row0 = m_blk * TILE_M + (int)cta_rank * BLOCK_M;   // first row of this CTA's 128-row slab
       const int row = row0 + row_in_tile;
       const bool row_ok = row < p.M;
@@ -306,9 +369,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       // this tile's column constants are in coltab[par]; everybody is done with coltab[par ^ 1]
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-      if (tile + n_workers < num_tiles) {
-        fetch_cols(tile + n_workers, par ^ 1);
-        fetch_stats(tile + n_workers, next_stats);
+      if (it + 1 < my_tiles) {
+        fetch_cols(it + 1, par ^ 1);
+        fetch_stats(it + 1, next_stats);
       }
       const float* tab0 = coltab + (par * 2) * BLOCK_N + col_group * COLS_PER_THREAD;
       const float* tab1 = tab0 + BLOCK_N;
@@ -319,6 +382,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + col_group * COLS_PER_THREAD);
 
       constexpr int N_CHUNKS = COLS_PER_THREAD / 32;
+      if (p.dbg & 2) {
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) tc::mbar_arrive_cluster(leader_tmem_empty + (uint32_t)(acc * 8));
+          else tc::mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        par ^= 1;
+        continue;
+      }
       uint32_t r[32], r_next[32];
       uint4 rv[4], rv_next[4];
       const uint4* res_row = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.N + col0);
@@ -364,20 +438,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             o[2 * i + 1] = pack_bf16(v[2], v[3]);
           }
         } else {
+          const uint64_t nmu2 = pack_f32x2(-mu, -mu), rstd2 = pack_f32x2(rstd, rstd);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 cc = *reinterpret_cast<const float4*>(tab0 + c + 4 * i);
             const float4 cd = *reinterpret_cast<const float4*>(tab1 + c + 4 * i);
-            const float c4[4] = {cc.x, cc.y, cc.z, cc.w};
-            const float d4[4] = {cd.x, cd.y, cd.z, cd.w};
-            float v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              v[j] = fmaf(rstd, fmaf(-mu, c4[j], __uint_as_float(r[4 * i + j])), d4[j]);
-              if (EPI == EPI_LNIN_GELU) v[j] = gelu_fast(v[j]);
+            // v = rstd * (acc - mu * c) + d on fp32 pairs
+            const uint64_t v01 = fma_f32x2(rstd2, fma_f32x2(nmu2, pack_f32x2(cc.x, cc.y), pack_f32x2(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]))),
+                                           pack_f32x2(cd.x, cd.y));
+            const uint64_t v23 = fma_f32x2(rstd2, fma_f32x2(nmu2, pack_f32x2(cc.z, cc.w), pack_f32x2(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]))),
+                                           pack_f32x2(cd.z, cd.w));
+            float v0, v1, v2, v3;
+            unpack_f32x2(v01, v0, v1);
+            unpack_f32x2(v23, v2, v3);
+            if (EPI == EPI_LNIN_GELU) {
+              o[2 * i] = gelu_f16x2(v0, v1);
+              o[2 * i + 1] = gelu_f16x2(v2, v3);
+            } else {
+              o[2 * i] = pack_bf16(v0, v1);
+              o[2 * i + 1] = pack_bf16(v2, v3);
             }
-            o[2 * i] = pack_bf16(v[0], v[1]);
-            o[2 * i + 1] = pack_bf16(v[2], v[3]);
           }
         }
         if (half == 0) {
@@ -399,8 +479,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (half == 1) {
           tc::fence_proxy_async();
           __syncwarp();
-          if (lane == 0) {
-            tc::tma_store_2d(&tmap_out, stage_buf + (size_t)sbuf * STAGING_BYTES, col0 + c - 32, row0 + quarter * 32);
+          if (lane == 0 && !(p.dbg & 1)) {
+            tc::tma_store_2d(&tmap_out, stage_buf + (size_t)sbuf * STAGING_BYTES, col0 + c - 32, ((p.dbg & 4) ? (int)(blockIdx.x & 1) * BLOCK_M : row0) + quarter * 32);
             tc::tma_store_commit();
           }
           if (STAGE_BUFS == 2) sbuf ^= 1;

@@ -220,5 +220,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
          | ((uint32_t)(m >> 4) << 24);    // m_dim
 }
 
+// ... fp16 x fp16 -> fp32 (a_format = b_format = F16 = 0)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
 }  // namespace tc
 }  // namespace drag

@@ -20,8 +20,9 @@ a = ap.parse_args()
 lib = _native.load()
 M, N, K = a.M, a.N, a.K
 g = torch.Generator(device="cuda").manual_seed(1)
-A = (torch.randn(M, K, device="cuda", generator=g) + 0.3).to(torch.bfloat16)
-W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+dt = torch.float16 if a.variant >= 20 else torch.bfloat16   # +20: fp16 operands (FFN-down)
+A = (torch.randn(M, K, device="cuda", generator=g) + 0.3).to(dt)
+W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(dt)
 colc = torch.randn(N, device="cuda", generator=g) * 0.2
 cold = torch.randn(N, device="cuda", generator=g) * 0.1
 gamma = torch.rand(N, device="cuda", generator=g) + 0.5

@@ -42,16 +42,21 @@ def _row_stats(x, parts=3):
 
 
 @pytest.mark.parametrize("variant,N,K", [(0, 1152, 384), (1, 1536, 384), (2, 384, 384), (2, 384, 1536), (0, 192, 64),
-                                         (10, 1152, 384), (11, 1536, 384), (12, 384, 384), (12, 384, 1536), (10, 192, 64)])
+                                         (10, 1152, 384), (11, 1536, 384), (12, 384, 384), (12, 384, 1536), (10, 192, 64),
+                                         (22, 384, 1536), (32, 384, 1536)])
 @pytest.mark.parametrize("M", [128, 77, 1000, 20000])
 def test_tcgen05_gemm_vs_torch(variant, N, K, M):
     """Each fused GEMM epilogue (LayerNorm folded, see drag_gemm.cuh) against plain torch fp32;
-    variants 10-12 are the CTA-pair (cta_group::2) forms of 0-2."""
+    variants 10-12 are the CTA-pair (cta_group::2) forms of 0-2, +20 = fp16 operands (the FFN-down
+    GEMM reads the fp16 GELU output).  The GELU epilogue (variant 1) writes fp16."""
     native, lib = _lib()
     code, variant = variant, variant % 10
+    f16_in = code >= 20
+    pair_form = (code % 20) >= 10
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N + variant)
-    a = _bf16(torch.randn(M, K, device="cuda", generator=g) + 0.3)
-    w = _bf16(torch.randn(N, K, device="cuda", generator=g) * 0.05)
+    a = torch.randn(M, K, device="cuda", generator=g) + 0.3
+    w = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    a, w = (a.half(), w.half()) if f16_in else (_bf16(a), _bf16(w))
     colc = torch.randn(N, device="cuda", generator=g) * 0.2
     cold = torch.randn(N, device="cuda", generator=g) * 0.1
     gamma = torch.rand(N, device="cuda", generator=g) + 0.5
@@ -62,7 +67,7 @@ def test_tcgen05_gemm_vs_torch(variant, N, K, M):
     width = normed.shape[1]
     mu = normed.float().mean(1, keepdim=True)
     rstd = torch.rsqrt(normed.float().var(1, unbiased=False, keepdim=True) + eps)
-    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16 if variant == 1 else torch.bfloat16)
     out_stats = torch.full((M, 3, 2), float("nan"), device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
     native.check(lib.drag_debug_gemm(0, code, a.data_ptr(), w.data_ptr(), colc.data_ptr(), cold.data_ptr(),
@@ -83,7 +88,7 @@ def test_tcgen05_gemm_vs_torch(variant, N, K, M):
     assert err <= 0.01 * scale + 0.02, (code, M, N, K, err, scale)
     assert (got - ref).abs().mean().item() <= 0.004 * max(ref.abs().mean().item(), 1e-3) + 1e-3
     if variant == 2:
-        tile, parts = (192, 2) if code >= 10 else (128, 3)   # the pair kernels leave the third slot untouched
+        tile, parts = (192, 2) if pair_form else (128, 3)   # the pair kernels leave the third slot untouched
         want = torch.stack([torch.stack((ref[:, i * tile:(i + 1) * tile].sum(1), (ref[:, i * tile:(i + 1) * tile] ** 2).sum(1)), 1)
                             for i in range(parts)], 1)
         assert torch.allclose(out_stats[:, :parts], want, rtol=2e-4, atol=2e-2), (out_stats[:, :parts] - want).abs().max()
