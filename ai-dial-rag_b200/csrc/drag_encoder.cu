@@ -202,10 +202,10 @@ struct drag_encoder {
   CUtensorMap tm_x, tm_y, tm_ctx, tm_h;           // A-operand loads (128 x 64 boxes)
   CUtensorMap ts_x, ts_y, ts_qkv, ts_h;           // epilogue stores (32 x 64 boxes)
   CUtensorMap tm_qkv_heads;                       // attention loads: 128 tokens x one head (32 columns)
-  // cta_group::2 (CTA-pair) GEMMs: bit 0 QKV, 1 out-proj, 2 FFN-up, 3 FFN-down.  Measured on B200 (same run,
+  // cta_group::2 (CTA-pair) GEMMs: bit 0 QKV, 1 out-proj, 2 FFN-up, 3 FFN-down; bit 4: weights-stationary FFN-up.  Measured on B200 (same run,
   // 262144 tokens): QKV 0.255 vs 0.267 ms, FFN-up 0.365 vs 0.375, FFN-down 0.339 vs 0.397 in favour of pairs;
   // the out-projection (N = K = 384, epilogue-bound) 0.178 vs 0.202 in favour of single CTAs.  DRAG_GEMM_PAIRS=<mask>.
-  int gemm_pairs = 13;
+  int gemm_pairs = 15;
   int attention_variant = 0;                      // 0 = mma.sync kernel (default: faster today), 1 = tcgen05 kernel (DRAG_ATTENTION=tc)
   // host-buffer path
   cudaStream_t stream = nullptr;
@@ -294,9 +294,10 @@ int upload_concat_f32(drag_encoder* e, float** dst, std::initializer_list<const 
 
 template <int BLOCK_N, int EPI, int EPI_WARPS, int STAGES, int CG, bool WS = false>
 int launch_gemm(const drag_encoder* e, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tout,
-                const gemm::GemmParams& p, cudaStream_t st) {
+                const CUtensorMap& tres, const gemm::GemmParams& p, cudaStream_t st) {
+  // tres: the residual rows as 32 x 64 boxes (EPI_RES; the other epilogues ignore it)
   auto kern = gemm::gemm_kernel<BLOCK_N, EPI, EPI_WARPS, STAGES, CG, WS>;
-  constexpr size_t smem = gemm::smem_bytes<BLOCK_N, STAGES, EPI_WARPS, CG, WS>();
+  constexpr size_t smem = gemm::smem_bytes<BLOCK_N, STAGES, EPI_WARPS, CG, WS, EPI>();
   if (WS) {
     DRAG_REQUIRE(p.K <= gemm::WS_K_BLOCKS * gemm::BLOCK_K, "weights-stationary GEMM holds at most K=%d (got %d)", gemm::WS_K_BLOCKS * gemm::BLOCK_K, p.K);
     DRAG_REQUIRE(e->sms / CG >= p.N / BLOCK_N, "weights-stationary GEMM needs at least one worker per column block");
@@ -315,7 +316,7 @@ int launch_gemm(const drag_encoder* e, const CUtensorMap& ta, const CUtensorMap&
   const int workers = e->sms / CG;   // CTAs, or CTA pairs (one pair per TPC)
   const int grid = CG * (tiles < workers ? tiles : workers);
   if (CG == 1) {
-    kern<<<grid, 64 + 32 * EPI_WARPS, smem, st>>>(ta, tw, tout, p);
+    kern<<<grid, 64 + 32 * EPI_WARPS, smem, st>>>(ta, tw, tout, tres, p);
     DRAG_CUDA_OK(cudaGetLastError());
   } else {
     cudaLaunchConfig_t cfg = {};
@@ -330,7 +331,7 @@ int launch_gemm(const drag_encoder* e, const CUtensorMap& ta, const CUtensorMap&
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    DRAG_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tw, tout, p));
+    DRAG_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tw, tout, tres, p));
   }
   return DRAG_OK;
 }
@@ -370,13 +371,14 @@ int attention_set_attributes() {
 // the four GEMM configurations of a layer
 #define DRAG_GEMM_QKV  launch_gemm<QKV_BLOCK_N, gemm::EPI_LNIN, 4, 4, 1>
 #define DRAG_GEMM_UP   launch_gemm<FFN_BLOCK_N, gemm::EPI_LNIN_GELU, 8, 3, 1>
-#define DRAG_GEMM_RES  launch_gemm<RES_BLOCK_N, gemm::EPI_RES, 8, 5, 1>
+#define DRAG_GEMM_RES  launch_gemm<RES_BLOCK_N, gemm::EPI_RES, 8, 4, 1>
 // ... and their CTA-pair (cta_group::2) forms: 256 x BLOCK_N tiles, half a W tile per CTA
 // (the K = 384 ones keep their W column block resident in shared memory: "weights stationary")
 #define DRAG_GEMM2_QKV launch_gemm<QKV_BLOCK_N, gemm::EPI_LNIN, 4, 6, 2, true>
 #define DRAG_GEMM2_UP  launch_gemm<FFN_BLOCK_N_PAIR, gemm::EPI_LNIN_GELU, 8, 4, 2>
-#define DRAG_GEMM2_RES launch_gemm<RES_BLOCK_N_PAIR, gemm::EPI_RES, 12, 6, 2>
-#define DRAG_GEMM2_RES_WS launch_gemm<RES_BLOCK_N_PAIR, gemm::EPI_RES, 12, 6, 2, true>
+#define DRAG_GEMM2_UP_WS launch_gemm<FFN_BLOCK_N_PAIR, gemm::EPI_LNIN_GELU, 8, 3, 2, true>
+#define DRAG_GEMM2_RES launch_gemm<RES_BLOCK_N_PAIR, gemm::EPI_RES, 12, 4, 2>
+#define DRAG_GEMM2_RES_WS launch_gemm<RES_BLOCK_N_PAIR, gemm::EPI_RES, 12, 3, 2, true>
 
 int forward_impl(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu, const int32_t* h_cu, int n_seq,
                  float* d_out, int stop_after_layer, float* d_hidden, cudaStream_t st) {
@@ -415,7 +417,7 @@ int forward_impl(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu, con
     p.N = 3 * HIDDEN; p.K = HIDDEN; p.colc = L.qkv_c; p.cold = L.qkv_d; p.in_stats = e->stats_x;
     {
       ProfScope prof(e, KC_GEMM_QKV, st);
-      rc = (e->gemm_pairs & 1) ? DRAG_GEMM2_QKV(e, e->tm_x, L.tp_qkv, e->ts_qkv, p, st) : DRAG_GEMM_QKV(e, e->tm_x, L.tm_qkv, e->ts_qkv, p, st);
+      rc = (e->gemm_pairs & 1) ? DRAG_GEMM2_QKV(e, e->tm_x, L.tp_qkv, e->ts_qkv, e->ts_qkv, p, st) : DRAG_GEMM_QKV(e, e->tm_x, L.tm_qkv, e->ts_qkv, e->ts_qkv, p, st);
     }
     if (rc) return rc;
     // attention
@@ -429,7 +431,7 @@ int forward_impl(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu, con
     p.residual = e->x; p.out_stats = e->stats_y;
     {
       ProfScope prof(e, KC_GEMM_OUT_LN, st);
-      rc = (e->gemm_pairs & 2) ? DRAG_GEMM2_RES_WS(e, e->tm_ctx, L.tp_o, e->ts_y, p, st) : DRAG_GEMM_RES(e, e->tm_ctx, L.tm_o, e->ts_y, p, st);
+      rc = (e->gemm_pairs & 2) ? DRAG_GEMM2_RES_WS(e, e->tm_ctx, L.tp_o, e->ts_y, e->ts_x, p, st) : DRAG_GEMM_RES(e, e->tm_ctx, L.tm_o, e->ts_y, e->ts_x, p, st);
     }
     if (rc) return rc;
     // h = gelu(LN_1(y) . W1^T + b_1)
@@ -437,7 +439,8 @@ int forward_impl(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu, con
     p.residual = nullptr; p.out_stats = nullptr;
     {
       ProfScope prof(e, KC_GEMM_UP_GELU, st);
-      rc = (e->gemm_pairs & 4) ? DRAG_GEMM2_UP(e, e->tm_y, L.tp_up, e->ts_h, p, st) : DRAG_GEMM_UP(e, e->tm_y, L.tm_up, e->ts_h, p, st);
+      rc = (e->gemm_pairs & 16) ? DRAG_GEMM2_UP_WS(e, e->tm_y, L.tp_up, e->ts_h, e->ts_h, p, st)
+           : (e->gemm_pairs & 4) ? DRAG_GEMM2_UP(e, e->tm_y, L.tp_up, e->ts_h, e->ts_h, p, st) : DRAG_GEMM_UP(e, e->tm_y, L.tm_up, e->ts_h, e->ts_h, p, st);
     }
     if (rc) return rc;
     // x_raw = h . W2^T + b_2 + LN_1(y_raw)   (+ row statistics of x_raw); LN_2 is applied by the consumers
@@ -445,7 +448,7 @@ int forward_impl(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu, con
     p.residual = e->y; p.out_stats = e->stats_x; p.f16_operands = 1;   // h and W2 are fp16
     {
       ProfScope prof(e, KC_GEMM_DOWN_LN, st);
-      rc = (e->gemm_pairs & 8) ? DRAG_GEMM2_RES(e, e->tm_h, L.tp_down, e->ts_x, p, st) : DRAG_GEMM_RES(e, e->tm_h, L.tm_down, e->ts_x, p, st);
+      rc = (e->gemm_pairs & 8) ? DRAG_GEMM2_RES(e, e->tm_h, L.tp_down, e->ts_x, e->ts_y, p, st) : DRAG_GEMM_RES(e, e->tm_h, L.tm_down, e->ts_x, e->ts_y, p, st);
     }
     if (rc) return rc;
   }
@@ -593,7 +596,7 @@ extern "C" int drag_encoder_create(const drag_bert_shape* shape, const float* co
     const char* v = getenv("DRAG_ATTENTION");
     if (v && strcmp(v, "tc") == 0) e->attention_variant = 1;
     const char* gm = getenv("DRAG_GEMM_PAIRS");
-    if (gm && gm[0] >= '0' && gm[0] <= '9') e->gemm_pairs = atoi(gm) & 15;
+    if (gm && gm[0] >= '0' && gm[0] <= '9') e->gemm_pairs = atoi(gm) & 31;
   }
 
   // host-buffer path: pinned staging + device mirrors
@@ -698,10 +701,12 @@ extern "C" int drag_debug_gemm(int device, int variant, const void* d_a, const v
   gemm::GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.colc = d_colc; p.cold = d_cold; p.gamma = d_gamma; p.in_stats = (const float2*)d_in_stats;
   p.inv_width = inv_width; p.ln_eps = ln_eps; p.residual = (const bf16*)d_residual; p.out_stats = (float2*)d_out_stats;
-  CUtensorMap ta, tw, tout;
+  CUtensorMap ta, tw, tout, tres;
   int rc = make_tmap(&ta, d_a, (uint64_t)M, (uint64_t)K, gemm::BLOCK_M);
   if (rc) return rc;
   if ((rc = make_tmap(&tout, d_out, (uint64_t)M, (uint64_t)N, gemm::STORE_ROWS))) return rc;
+  tres = tout;
+  if (d_residual && (rc = make_tmap(&tres, d_residual, (uint64_t)M, (uint64_t)N, gemm::STORE_ROWS))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (const char* dbg = getenv("DRAG_GEMM_DBG")) p.dbg = atoi(dbg);
   if (variant >= 20) { p.f16_operands = 1; variant -= 20; }   // A and W hold fp16
@@ -709,27 +714,27 @@ extern "C" int drag_debug_gemm(int device, int variant, const void* d_a, const v
     case 0:
       DRAG_REQUIRE(N % QKV_BLOCK_N == 0 && d_colc, "drag_debug_gemm: variant 0 needs N %% %d == 0 and colc", QKV_BLOCK_N);
       if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, QKV_BLOCK_N))) return rc;
-      return DRAG_GEMM_QKV(&fake, ta, tw, tout, p, st);
+      return DRAG_GEMM_QKV(&fake, ta, tw, tout, tres, p, st);
     case 1:
       DRAG_REQUIRE(N % FFN_BLOCK_N == 0 && d_colc, "drag_debug_gemm: variant 1 needs N %% %d == 0 and colc", FFN_BLOCK_N);
       if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, FFN_BLOCK_N))) return rc;
-      return DRAG_GEMM_UP(&fake, ta, tw, tout, p, st);
+      return DRAG_GEMM_UP(&fake, ta, tw, tout, tres, p, st);
     case 2:
       DRAG_REQUIRE(N == HIDDEN && d_gamma && d_residual && d_out_stats, "drag_debug_gemm: variant 2 needs N=384, gamma, residual, out_stats");
       if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, RES_BLOCK_N))) return rc;
-      return DRAG_GEMM_RES(&fake, ta, tw, tout, p, st);
+      return DRAG_GEMM_RES(&fake, ta, tw, tout, tres, p, st);
     case 10:
       DRAG_REQUIRE(N % QKV_BLOCK_N == 0 && d_colc, "drag_debug_gemm: variant 10 needs N %% %d == 0 and colc", QKV_BLOCK_N);
       if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, QKV_BLOCK_N / 2))) return rc;
-      return DRAG_GEMM2_QKV(&fake, ta, tw, tout, p, st);
+      return DRAG_GEMM2_QKV(&fake, ta, tw, tout, tres, p, st);
     case 11:
       DRAG_REQUIRE(N % FFN_BLOCK_N_PAIR == 0 && d_colc, "drag_debug_gemm: variant 11 needs N %% %d == 0 and colc", FFN_BLOCK_N_PAIR);
       if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, FFN_BLOCK_N_PAIR / 2))) return rc;
-      return DRAG_GEMM2_UP(&fake, ta, tw, tout, p, st);
+      return DRAG_GEMM2_UP(&fake, ta, tw, tout, tres, p, st);
     case 12:
       DRAG_REQUIRE(N == HIDDEN && d_gamma && d_residual && d_out_stats, "drag_debug_gemm: variant 12 needs N=384, gamma, residual, out_stats");
       if ((rc = make_tmap(&tw, d_w, (uint64_t)N, (uint64_t)K, RES_BLOCK_N_PAIR / 2))) return rc;
-      return K <= gemm::WS_K_BLOCKS * gemm::BLOCK_K ? DRAG_GEMM2_RES_WS(&fake, ta, tw, tout, p, st) : DRAG_GEMM2_RES(&fake, ta, tw, tout, p, st);
+      return K <= gemm::WS_K_BLOCKS * gemm::BLOCK_K ? DRAG_GEMM2_RES_WS(&fake, ta, tw, tout, tres, p, st) : DRAG_GEMM2_RES(&fake, ta, tw, tout, tres, p, st);
     default:
       return fail(DRAG_ERR_INVALID, "drag_debug_gemm: unknown variant %d", variant);
   }

@@ -79,19 +79,21 @@ struct Cfg {
   static_assert(STAGE_BYTES % 1024 == 0 && (B_STAGE_BYTES / 2) % 1024 == 0, "stage must keep 1024-byte alignment");
 };
 
-template <int BLOCK_N, int EPI_WARPS>
-constexpr int stage_bufs() { return (BLOCK_N / (EPI_WARPS / 4)) > STORE_COLS ? 2 : 1; }
+// staging buffers per epilogue warp: a warp with several store groups per tile double buffers; the residual
+// epilogue always does (the next tile's residual box is TMA-loaded into the other buffer a tile ahead)
+template <int BLOCK_N, int EPI_WARPS, int EPI = EPI_LNIN>
+constexpr int stage_bufs() { return (EPI == EPI_RES || (BLOCK_N / (EPI_WARPS / 4)) > STORE_COLS) ? 2 : 1; }
 
 constexpr int WS_K_BLOCKS = 6;   // weights-stationary kernels hold K = 384 (6 k-blocks) of their W column block
 
-template <int BLOCK_N, int STAGES, int EPI_WARPS, int CG = 1, bool WS = false>
+template <int BLOCK_N, int STAGES, int EPI_WARPS, int CG = 1, bool WS = false, int EPI = EPI_LNIN>
 constexpr size_t smem_bytes() {
   // ring (A + W, or A only next to the resident W block) + per-warp store staging + [barriers, tmem pointer,
   // statistics exchange | 4 KB] + [column constants: 2 tiles x 2 vectors x BLOCK_N floats <= 4 KB] + slack for
   // manual 1024-byte alignment
   return (WS ? (size_t)STAGES * A_STAGE_BYTES + (size_t)WS_K_BLOCKS * (Cfg<BLOCK_N>::B_STAGE_BYTES / CG)
              : (size_t)STAGES * (A_STAGE_BYTES + Cfg<BLOCK_N>::B_STAGE_BYTES / CG)) +
-         (size_t)EPI_WARPS * stage_bufs<BLOCK_N, EPI_WARPS>() * STAGING_BYTES + 8192 + 1024;
+         (size_t)EPI_WARPS * stage_bufs<BLOCK_N, EPI_WARPS, EPI>() * STAGING_BYTES + 8192 + 1024;
 }
 
 // Packed fp32 pairs (FFMA2: one instruction per two lanes of the epilogue arithmetic)
@@ -150,7 +152,7 @@ __device__ __forceinline__ void row_stats(const float2* stats, int row, bool ok,
 template <int BLOCK_N, int EPI, int EPI_WARPS, int STAGES, int CG, bool WS>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-            const __grid_constant__ CUtensorMap tmap_out, GemmParams p) {
+            const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res, GemmParams p) {
   using C = Cfg<BLOCK_N>;
   static_assert(CG == 1 || CG == 2, "single CTAs or CTA pairs");
   constexpr int B_BYTES = C::B_STAGE_BYTES / CG;          // this CTA's part of the W tile (one k-block)
@@ -161,7 +163,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   static_assert(EPI != EPI_RES || EPI_WARPS <= 12, "the statistics exchange of EPI_RES handles at most three column groups");
   constexpr int COL_GROUPS = EPI_WARPS / 4;
   constexpr int COLS_PER_THREAD = BLOCK_N / COL_GROUPS;
-  constexpr int STAGE_BUFS = stage_bufs<BLOCK_N, EPI_WARPS>();   // a warp with several store groups per tile double buffers
+  constexpr int STAGE_BUFS = stage_bufs<BLOCK_N, EPI_WARPS, EPI>();
+  static_assert(EPI != EPI_RES || COLS_PER_THREAD == STORE_COLS, "the residual epilogue handles one 64-column group per warp and tile");
   static_assert(COLS_PER_THREAD % STORE_COLS == 0, "epilogue stores 64-column groups");
 
   extern __shared__ uint8_t smem_raw[];
@@ -174,7 +177,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint64_t* w_bar = tmem_empty_bar + 2;                    // WS: the resident W block has landed
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_bar + 1);
+  uint64_t* res_bar = w_bar + 1;                           // RES: [EPI_WARPS][2] the warp's residual box has landed in staging buffer b
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 32);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -199,6 +203,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     tc::tma_prefetch_desc(&tmap_a);
     tc::tma_prefetch_desc(&tmap_w);
     tc::tma_prefetch_desc(&tmap_out);
+    if (EPI == EPI_RES) tc::tma_prefetch_desc(&tmap_res);
     for (int s = 0; s < STAGES; ++s) {
       tc::mbar_init(&full_bar[s], 1);
       tc::mbar_init(&empty_bar[s], 1);
@@ -208,6 +213,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       tc::mbar_init(&tmem_empty_bar[s], CG * EPI_WARPS);   // the leader's collects both CTAs' epilogue warps
     }
     tc::mbar_init(w_bar, 1);
+    for (int s = 0; s < 2 * EPI_WARPS; ++s) tc::mbar_init(&res_bar[s], 1);
     tc::fence_barrier_init();
   }
   if (CG == 2) tc::cluster_sync_all();   // the peer's barriers must exist before anything signals them
@@ -347,10 +353,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
     };
 
+    // RES: the warp's 32 x 64 box of raw residual rows arrives by TMA in the staging buffer the output
+    // will be written to (same box, same swizzle: the epilogue works in place), one tile ahead
+    auto fetch_residual = [&](int it_, int buf_) {
+      if (lane == 0) {
+        tc::mbar_arrive_expect_tx(&res_bar[2 * ew + buf_], STAGING_BYTES);
+        tc::tma_load_2d(&tmap_res, &res_bar[2 * ew + buf_], stage_buf + (size_t)buf_ * STAGING_BYTES, tile_n(it_) * BLOCK_N + col_group * COLS_PER_THREAD,
+                        tile_m(it_) * TILE_M + (int)cta_rank * BLOCK_M + quarter * 32);
+      }
+    };
     float2 next_stats[STATS_PARTS];
     if (my_tiles > 0) {
       fetch_cols(0, 0);
       fetch_stats(0, next_stats);
+      if (EPI == EPI_RES) fetch_residual(0, 0);
     }
     for (int it = 0; it < my_tiles; ++it) {
       const int m_blk = tile_m(it), n_blk = tile_n(it);
@@ -372,6 +388,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       if (it + 1 < my_tiles) {
         fetch_cols(it + 1, par ^ 1);
         fetch_stats(it + 1, next_stats);
+        if (EPI == EPI_RES) {
+          // the other staging buffer was last read by the TMA store of tile it-1 (the newest committed group)
+          if (lane == 0) tc::tma_store_wait_read();
+          fetch_residual(it + 1, sbuf ^ 1);
+        }
       }
       const float* tab0 = coltab + (par * 2) * BLOCK_N + col_group * COLS_PER_THREAD;
       const float* tab1 = tab0 + BLOCK_N;
@@ -394,13 +415,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         continue;
       }
       uint32_t r[32], r_next[32];
-      uint4 rv[4], rv_next[4];
-      const uint4* res_row = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.N + col0);
+      uint4 rv[4];
       tc::tmem_ld32(t_row, r);
-      if (EPI == EPI_RES) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) rv[i] = row_ok ? __ldg(res_row + i) : make_uint4(0, 0, 0, 0);
-      }
+      if (EPI == EPI_RES) tc::mbar_wait(&res_bar[2 * ew + sbuf], (uint32_t)((it >> 1) & 1));
 #pragma unroll
       for (int ch = 0; ch < N_CHUNKS; ++ch) {
         const int c = ch * 32;
@@ -409,13 +426,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (ch + 1 < N_CHUNKS) {
           // next 32 columns: in flight during this chunk's math
           tc::tmem_ld32(t_row + c + 32, r_next);
-          if (EPI == EPI_RES) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) rv_next[i] = row_ok ? __ldg(res_row + (c + 32) / 8 + i) : make_uint4(0, 0, 0, 0);
-          }
         }
         uint32_t o[16];
         if (EPI == EPI_RES) {
+          // this chunk's 32 residual values: 16-byte chunk j of row r lives at chunk (j ^ (r & 7))
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t chunk = (uint32_t)((half * 4 + j) ^ (lane & 7));
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rv[j].x), "=r"(rv[j].y), "=r"(rv[j].z), "=r"(rv[j].w)
+                         : "r"(stage_row + (uint32_t)(sbuf * STAGING_BYTES) + chunk * 16u) : "memory");
+            if (!row_ok) rv[j] = make_uint4(0, 0, 0, 0);   // rows past M hold stale data
+          }
           const uint32_t* rw = reinterpret_cast<const uint32_t*>(rv);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -460,8 +481,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
           }
         }
-        if (half == 0) {
+        if (half == 0 && EPI != EPI_RES) {
           // the TMA store that last read this staging buffer must be done with it
+          // (RES: already waited for before the residual box was loaded into it)
           if (lane == 0) {
             if (STAGE_BUFS == 2) tc::tma_store_wait_read_1();
             else tc::tma_store_wait_read();
@@ -488,10 +510,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (ch + 1 < N_CHUNKS) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) r[i] = r_next[i];
-          if (EPI == EPI_RES) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) rv[i] = rv_next[i];
-          }
         }
       }
       // all TMEM reads of this warp are complete -> hand the accumulator back to the MMA warp
