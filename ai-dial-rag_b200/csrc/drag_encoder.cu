@@ -20,6 +20,7 @@
 
 #include "drag_attention.cuh"
 #include "drag_attention_tc.cuh"
+#include "drag_attention_tc2.cuh"
 #include "drag_common.cuh"
 #include "drag_gemm.cuh"
 
@@ -340,7 +341,17 @@ int launch_gemm(const drag_encoder* e, const CUtensorMap& ta, const CUtensorMap&
 int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* qkv, bf16* ctx, const int32_t* d_cu,
                      int n_seq, int max_len, int heads, cudaStream_t st) {
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)HEAD_DIM);
-  if (variant == 1) {
+  if (variant == 2) {
+    const size_t smem = attn_tc2::smem_bytes(max_len);
+    const int items = heads * n_seq;
+    int sms = 148;
+    {
+      int dev = 0;
+      if (cudaGetDevice(&dev) == cudaSuccess && sm_count(dev) > 0) sms = sm_count(dev);
+    }
+    attn_tc2::attention_tc2_kernel<<<items < sms ? items : sms, attn_tc2::THREADS, smem, st>>>(
+        tm_qkv_heads, ctx, d_cu, n_seq, heads, (max_len + attn_tc::TILE - 1) / attn_tc::TILE, attn_tc2::item_stages(max_len), scale_log2);
+  } else if (variant == 1) {
     const size_t smem = attn_tc::smem_bytes(max_len);
     const int items = heads * n_seq;
     int sms = 148;
@@ -365,6 +376,7 @@ int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* q
 int attention_set_attributes() {
   DRAG_CUDA_OK(cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::smem_bytes(512)));
   DRAG_CUDA_OK(cudaFuncSetAttribute(attn_tc::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_tc::smem_bytes(512)));
+  DRAG_CUDA_OK(cudaFuncSetAttribute(attn_tc2::attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_tc2::smem_bytes(256)));   // the largest (3 stages of 2-tile items)
   return DRAG_OK;
 }
 
@@ -595,6 +607,7 @@ extern "C" int drag_encoder_create(const drag_bert_shape* shape, const float* co
   {
     const char* v = getenv("DRAG_ATTENTION");
     if (v && strcmp(v, "tc") == 0) e->attention_variant = 1;
+    if (v && strcmp(v, "tc2") == 0) e->attention_variant = 2;
     const char* gm = getenv("DRAG_GEMM_PAIRS");
     if (gm && gm[0] >= '0' && gm[0] <= '9') e->gemm_pairs = atoi(gm) & 31;
   }
@@ -744,13 +757,13 @@ extern "C" int drag_debug_attention(int device, int variant, const void* d_qkv, 
                                     int n_seq, int n_tokens, int max_len, int heads, void* stream) {
   DRAG_REQUIRE(d_qkv && d_ctx && d_cu_seqlens && n_seq >= 1 && heads >= 1 && n_tokens >= 1, "drag_debug_attention: bad arguments");
   DRAG_REQUIRE(max_len >= 1 && max_len <= 512, "drag_debug_attention: max_len must be in 1..512");
-  DRAG_REQUIRE(variant == 0 || variant == 1, "drag_debug_attention: variant 0 (mma.sync) or 1 (tcgen05)");
+  DRAG_REQUIRE(variant >= 0 && variant <= 2, "drag_debug_attention: variant 0 (mma.sync), 1 (tcgen05) or 2 (tcgen05, exact single-pass softmax)");
   DeviceGuard guard(device);
   if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_debug_attention: cannot select device %d", device);
   int rc = attention_set_attributes();
   if (rc) return rc;
   CUtensorMap tm;
-  if (variant == 1 &&
+  if (variant >= 1 &&
       (rc = make_tmap_bf16_box(&tm, d_qkv, (uint64_t)n_tokens, (uint64_t)3 * heads * HEAD_DIM, attn_tc::TILE, attn_tc::HEAD_DIM)))
     return rc;
   return launch_attention(variant, tm, (const bf16*)d_qkv, (bf16*)d_ctx, d_cu_seqlens, n_seq, max_len, heads, (cudaStream_t)stream);
