@@ -233,9 +233,12 @@ int drag_topk_batch(int device, const void* d_matrix, int dtype, const void* d_s
  * OUT[M,N] = epilogue(A[M,K] . W[N,K]^T), bf16 in/out, fp32 accumulate (tcgen05), LayerNorm folded:
  * with (mu, rstd) of a row taken from d_in_stats ([M][3] float2 partial (sum, sum^2), width 1/inv_width)
  *   variant 0: out = rstd*(acc - mu*colc) + cold                       (N % 192 == 0)
- *   variant 1: out = gelu(rstd*(acc - mu*colc) + cold)                 (N % 256 == 0)
+ *   variant 1: out = gelu(rstd*(acc - mu*colc) + cold), stored as FP16  (N % 256 == 0)
  *   variant 2: out = acc + cold + (residual - mu)*rstd*gamma, and the row's per-128-column-tile
  *              (sum, sum^2) of `out` -> d_out_stats [M][3]             (N == 384)
+ *   +10: the CTA-pair (cta_group::2) form (variant 12 leaves the third statistics slot untouched: 192-column tiles);
+ *   +20: A and W hold fp16 instead of bf16 (the FFN-down GEMM reads the fp16 GELU output).
+ * DRAG_GEMM_DBG=<mask> (probes only): 1 no output stores, 2 no epilogue, 4 stores land on one row block.
  */
 int drag_debug_gemm(int device, int variant, const void* d_a, const void* d_w, const float* d_colc,
                     const float* d_cold, const float* d_gamma, const void* d_in_stats, const void* d_residual,
@@ -243,7 +246,8 @@ int drag_debug_gemm(int device, int variant, const void* d_a, const void* d_w, c
                     void* stream);
 
 /* ctx[T, heads*32] = softmax(Q K^T / sqrt(32)) V per packed sequence; d_qkv is bf16 [n_tokens, 3*heads*32].
- * variant 0 = mma.sync kernel (the encoder's default), 1 = tcgen05 kernel (DRAG_ATTENTION=tc). */
+ * variant 0 = mma.sync kernel (the encoder's default), 1 = tcgen05 kernel (DRAG_ATTENTION=tc),
+ * 2 = second tcgen05 design: ping-pong score tiles, four threads per row (DRAG_ATTENTION=tc2). */
 int drag_debug_attention(int device, int variant, const void* d_qkv, void* d_ctx, const int32_t* d_cu_seqlens,
                          int n_seq, int n_tokens, int max_len, int heads, void* stream);
 
