@@ -509,12 +509,18 @@ def main() -> None:
     att["exp_per_s"] = exp_per_launch / (att["avg_ms"] / 1e3)
     att["mufu_peak_exp_per_s"] = 16.0 * 148 * clk_hz   # measured: 16 ex2 / clock / SM (scripts/ubench/pipes.cu)
     att["frac_of_mufu_peak"] = att["exp_per_s"] / att["mufu_peak_exp_per_s"]
-    att["note"] = ("head_dim 32: 1 exponential per 128 flop, so the MUFU pipe (16/clk/SM) bounds this op at "
-                   "~4x less time than it takes today and the tensor pipe is not the roofline; see DESIGN.md")
+    att["note"] = ("head_dim 32: 1 exponential per 128 flop; the MUFU pipe (16 ex2/clk/SM, measured) and the legacy "
+                   "mma.sync pipe (2048 flop/clk/SM) each bound this op at the same ~0.18 ms per 1024 chunks, so "
+                   "frac_of_mufu_peak is its roofline fraction; see DESIGN.md section 4")
     roofline = {
         "kernel": "gemm_kernel (tcgen05 GEMM template: QKV, out-proj, FFN-up, FFN-down instantiations)",
         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-        "frac": achieved / peaks["tflops_sustained"], "traffic": None,
+        "frac": achieved / peaks["tflops_sustained"],
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the four instantiations, from the
+        # ncu --set full capture in profiles/r01_e_ncu_full_summary.md (taken at 65 536 tokens, scaled by tokens)
+        "traffic": 191.3e6 * tokens / 65536.0,
+        "traffic_source": "profiles/r01_e_ncu_full_summary.md (ncu --set full, 65 536 tokens, scaled linearly in tokens); "
+                          "algorithmic operand+output bytes per launch average 906 MB at 262 144 tokens",
         "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
         "flop_per_launch": gemm_flop_per_layer / 4.0, "avg_launch_ms": gemm_ms / gemm_launches,
         "share_of_step": gemm_ms / kernel_ms,
