@@ -747,6 +747,31 @@ __global__ void query_prep_kernel(const double* queries, int nq, int dim, double
   q_norm[q] = fmax(sqrt(s), 1e-8);
 }
 
+// One block per query: the query is staged in shared memory by the whole block (coalesced), then one thread
+// forms the two sums in their fixed orders (numpy pairwise for q_sq) without a global-load latency per element.
+__global__ void __launch_bounds__(128) query_prep_smem_kernel(const double* queries, int nq, int dim, double* q_sq, double* q_norm) {
+  extern __shared__ __align__(16) double qs[];
+  const int q = blockIdx.x;
+  if (q >= nq) return;
+  const double* p = queries + (size_t)q * dim;
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) qs[i] = p[i];
+  __syncthreads();
+  // the two sums run side by side in two warps (each is one dependent float64 chain)
+  if (threadIdx.x == 0) q_sq[q] = pairwise_sq_f64(qs, dim);
+  if (threadIdx.x == 32) {
+    double s = 0.0;
+    for (int i = 0; i < dim; ++i) s = __fma_rn(qs[i], qs[i], s);
+    q_norm[q] = fmax(sqrt(s), 1e-8);
+  }
+}
+
+static int launch_query_prep(const double* d_queries, int nq, int dim, double* q_sq, double* q_norm, cudaStream_t st) {
+  if ((size_t)dim * 8 <= 48 * 1024) query_prep_smem_kernel<<<nq, 128, (size_t)dim * 8, st>>>(d_queries, nq, dim, q_sq, q_norm);
+  else query_prep_kernel<<<(nq + 63) / 64, 64, 0, st>>>(d_queries, nq, dim, q_sq, q_norm);
+  DRAG_CUDA_OK(cudaGetLastError());
+  return DRAG_OK;
+}
+
 __global__ void rows_to_chunks_kernel(const long long* rows, long long n, const long long* doc_offsets, int n_docs,
                                       const long long* chunk_ids, long long* out_doc, long long* out_chunk) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -818,6 +843,7 @@ static int next_pow2_min32(int k) {
 
 constexpr int MAX_K = 2048;
 constexpr int MERGE_WARPS = 8;
+constexpr int MERGE_WARPS_WIDE = 32;   // short lists: every warp walks fewer of the per-CTA lists (their loads are serial per warp)
 constexpr size_t SMEM_BUDGET = 200 * 1024;
 
 struct Plan {
@@ -918,6 +944,21 @@ static int launch_scan(int metric, const ScanArgs& a, const Plan& p, bool vec_ok
   if (p.qb == 1 && p.nwarps == 8) return launch_scan_m<T, 1, 8>(metric, a, p, vec_ok, st);
   if (p.qb == 1 && p.nwarps == 4) return launch_scan_m<T, 1, 4>(metric, a, p, vec_ok, st);
   return fail(DRAG_ERR_UNSUPPORTED, "no scan kernel for qb=%d nwarps=%d", p.qb, p.nwarps);
+}
+
+template <bool FROM_DOUBLE>
+static int launch_merge(const MergeArgs& m, int n_blocks, cudaStream_t st) {
+  const size_t wide = (size_t)MERGE_WARPS_WIDE * list_bytes(m.kpad, 8);
+  if (wide <= SMEM_BUDGET) {
+    DRAG_CUDA_OK(cudaFuncSetAttribute(merge_kernel<FROM_DOUBLE, MERGE_WARPS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide));
+    merge_kernel<FROM_DOUBLE, MERGE_WARPS_WIDE><<<n_blocks, MERGE_WARPS_WIDE * 32, wide, st>>>(m);
+  } else {
+    const size_t smem = (size_t)MERGE_WARPS * list_bytes(m.kpad, 8);
+    DRAG_CUDA_OK(cudaFuncSetAttribute(merge_kernel<FROM_DOUBLE, MERGE_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_kernel<FROM_DOUBLE, MERGE_WARPS><<<n_blocks, MERGE_WARPS * 32, smem, st>>>(m);
+  }
+  DRAG_CUDA_OK(cudaGetLastError());
+  return DRAG_OK;
 }
 
 struct Workspace {
@@ -1179,8 +1220,7 @@ extern "C" int drag_distances(int device, const void* d_matrix, int dtype, int64
   cudaStream_t st = (cudaStream_t)stream;
   double* q_sq = (double*)d_scratch16;
   double* q_norm = q_sq + 1;
-  query_prep_kernel<<<1, 32, 0, st>>>(d_query, 1, dim, q_sq, q_norm);
-  DRAG_CUDA_OK(cudaGetLastError());
+  { int rc = launch_query_prep(d_query, 1, dim, q_sq, q_norm, st); if (rc) return rc; }
   if (dtype == DRAG_F32)
     return launch_distances<float>(metric, (const float*)d_matrix, n_rows, dim, d_row_sqnorm, d_query, q_sq, q_norm, d_out, st);
   return launch_distances<__nv_bfloat16>(metric, (const __nv_bfloat16*)d_matrix, n_rows, dim, d_row_sqnorm, d_query, q_sq, q_norm, d_out, st);
@@ -1218,8 +1258,7 @@ extern "C" int drag_topk(int device, const void* d_matrix, int dtype, int64_t n_
   size_t need = carve(p, n_queries, d_workspace, &ws);
   DRAG_REQUIRE(workspace_bytes >= need, "drag_topk: workspace too small (%zu < %zu)", workspace_bytes, need);
 
-  query_prep_kernel<<<(n_queries + 63) / 64, 64, 0, st>>>(d_queries, n_queries, dim, ws.q_sq, ws.q_norm);
-  DRAG_CUDA_OK(cudaGetLastError());
+  { int rc = launch_query_prep(d_queries, n_queries, dim, ws.q_sq, ws.q_norm, st); if (rc) return rc; }
 
   const size_t esz = dtype == DRAG_F32 ? 4 : 2;
   const bool vec_ok = ((size_t)dim * esz) % 16 == 0 && ((uintptr_t)d_matrix % 16) == 0;
@@ -1228,9 +1267,6 @@ extern "C" int drag_topk(int device, const void* d_matrix, int dtype, int64_t n_
   long long want = (n_rows + rows_per_cta - 1) / rows_per_cta;
   if (want < 1) want = 1;
   if (want < p.grid) p.grid = (int)want;
-
-  const size_t merge_smem = (size_t)MERGE_WARPS * list_bytes(p.kpad, 8);
-  DRAG_CUDA_OK(cudaFuncSetAttribute(merge_kernel<false, MERGE_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem));
 
   for (int q0 = 0; q0 < n_queries; q0 += p.qb) {
     ScanArgs a;
@@ -1248,8 +1284,7 @@ extern "C" int drag_topk(int device, const void* d_matrix, int dtype, int64_t n_
     m.n_lists = p.grid; m.list_len = p.kpad; m.nq = a.nq; m.k = k; m.kpad = p.kpad;
     m.out_dist = d_out_dist + (size_t)q0 * k; m.out_row = (long long*)d_out_row + (size_t)q0 * k;
     m.out_count = d_out_count + q0;
-    merge_kernel<false, MERGE_WARPS><<<a.nq, MERGE_WARPS * 32, merge_smem, st>>>(m);
-    DRAG_CUDA_OK(cudaGetLastError());
+    if ((rc = launch_merge<false>(m, a.nq, st)) != DRAG_OK) return rc;
   }
   return DRAG_OK;
 }
@@ -1268,9 +1303,7 @@ extern "C" int drag_topk_merge(int device, const double* d_in_dist, const int64_
   m.in_keys = nullptr; m.in_rows = (const long long*)d_in_row; m.in_dist = d_in_dist; m.in_count = d_in_count;
   m.n_lists = n_shards; m.list_len = 0; m.nq = n_queries; m.k = k; m.kpad = next_pow2_min32(k);
   m.out_dist = d_out_dist; m.out_row = (long long*)d_out_row; m.out_count = d_out_count;
-  const size_t merge_smem = (size_t)MERGE_WARPS * list_bytes(m.kpad, 8);
-  DRAG_CUDA_OK(cudaFuncSetAttribute(merge_kernel<true, MERGE_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem));
-  merge_kernel<true, MERGE_WARPS><<<n_queries, MERGE_WARPS * 32, merge_smem, st>>>(m);
+  { int rc = launch_merge<true>(m, n_queries, st); if (rc) return rc; }
   DRAG_CUDA_OK(cudaGetLastError());
   return DRAG_OK;
 }
@@ -1398,8 +1431,7 @@ static int run_batch(int device, const void* d_matrix, int dtype, const void* d_
     plan.colvec = d_row_sqnorm;
   }
 
-  query_prep_kernel<<<(n_queries + 63) / 64, 64, 0, st>>>(d_queries, n_queries, dim, ws.q_sq, ws.q_norm);
-  DRAG_CUDA_OK(cudaGetLastError());
+  { int rc = launch_query_prep(d_queries, n_queries, dim, ws.q_sq, ws.q_norm, st); if (rc) return rc; }
   {
     const size_t n = (size_t)q_pad * dim;
     tcs::queries_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_queries, n_queries, q_pad, dim, ws.q_bf16);
