@@ -132,7 +132,10 @@ __device__ __forceinline__ void attend_block(const __nv_bfloat16* vs, int key0, 
         float v = lm[mt][h];
         v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
         v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
-        const float mn = fmaxf(m[mt][h], v);
+        // the decision is per ROW (v is the row's block maximum in all four lanes of its quad), so a row's
+        // sequence of references -- and with it every bit of its result -- depends on that row's scores only,
+        // not on which rows share its warp (tests/test_encoder_gpu.py::test_batch_composition_invariance)
+        const float mn = v > m[mt][h] + lazy_raw ? v : m[mt][h];
         const float corr = fast_exp2((m[mt][h] - mn) * scale_log2);
         m[mt][h] = mn;
 #pragma unroll
@@ -240,7 +243,8 @@ __device__ __forceinline__ void attend_rows(const __nv_bfloat16* ks, const __nv_
 
 // qkv : [T, 3*hidden] bf16, per token [Q(hidden) | K(hidden) | V(hidden)], head h at columns h*32
 // ctx : [T, hidden] bf16
-// grid = (heads * ceil(max_len / 256), n_seq): blockIdx.x = q_tile * heads + head; block = WARPS*32;
+// grid = (heads * ceil(max_len / rows_per_cta), n_seq): blockIdx.x = q_tile * heads + head; block = WARPS*32;
+// rows_per_cta = 256 (throughput: K/V staged once per 256 queries) or 128 / 64 (few sequences: more CTAs);
 // dynamic smem = smem_bytes(max_len)
 __host__ __device__ inline size_t smem_bytes(int max_len) {
   const int s_pad = (max_len + 31) & ~31;
@@ -250,16 +254,16 @@ __host__ __device__ inline size_t smem_bytes(int max_len) {
 
 __global__ void __launch_bounds__(WARPS * 32, 3)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx,
-                 const int* __restrict__ cu_seqlens, int heads, float scale_log2) {
+                 const int* __restrict__ cu_seqlens, int heads, float scale_log2, int rows_per_cta) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int head = blockIdx.x % heads;
   const int q_tile = blockIdx.x / heads;
   const int seq = blockIdx.y;
   const int tok0 = cu_seqlens[seq];
   const int S = cu_seqlens[seq + 1] - tok0;
-  const int row0 = q_tile * ROWS_PER_CTA;
+  const int row0 = q_tile * rows_per_cta;
   if (row0 >= S) return;
-  const int rows = min(S - row0, ROWS_PER_CTA);
+  const int rows = min(S - row0, rows_per_cta);
   const int hidden = heads * HEAD_DIM;
   const int s_pad = (S + 31) & ~31;
   const int q_pad = (rows + 31) & ~31;

@@ -363,10 +363,13 @@ int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* q
         tm_qkv_heads, ctx, d_cu, n_seq, heads, (max_len + attn_tc::TILE - 1) / attn_tc::TILE, attn_tc::item_stages(max_len), scale_log2);
   } else {
     const size_t smem = attn::smem_bytes(max_len);
-    const int q_tiles = (max_len + attn::ROWS_PER_CTA - 1) / attn::ROWS_PER_CTA;
+    // few sequences (the query path): smaller query tiles so that the launch still fills the GPU
+    int rows_per_cta = attn::ROWS_PER_CTA;
+    while (rows_per_cta > 64 && (long long)heads * n_seq * ((max_len + rows_per_cta - 1) / rows_per_cta) < 148) rows_per_cta >>= 1;
+    const int q_tiles = (max_len + rows_per_cta - 1) / rows_per_cta;
     for (int s0 = 0; s0 < n_seq; s0 += 65535) {   // gridDim.y limit
       const int n = n_seq - s0 < 65535 ? n_seq - s0 : 65535;
-      attn::attention_kernel<<<dim3(heads * q_tiles, n), attn::WARPS * 32, smem, st>>>(qkv, ctx, d_cu + s0, heads, scale_log2);
+      attn::attention_kernel<<<dim3(heads * q_tiles, n), attn::WARPS * 32, smem, st>>>(qkv, ctx, d_cu + s0, heads, scale_log2, rows_per_cta);
     }
   }
   DRAG_CUDA_OK(cudaGetLastError());
@@ -374,9 +377,15 @@ int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* q
 }
 
 int attention_set_attributes() {
+  // the shared-memory need is not monotonic in the sequence length (fewer stages for longer items): take the maximum
+  size_t tc_max = 0, tc2_max = 0;
+  for (int len = 128; len <= 512; len += 128) {
+    tc_max = attn_tc::smem_bytes(len) > tc_max ? attn_tc::smem_bytes(len) : tc_max;
+    tc2_max = attn_tc2::smem_bytes(len) > tc2_max ? attn_tc2::smem_bytes(len) : tc2_max;
+  }
   DRAG_CUDA_OK(cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::smem_bytes(512)));
-  DRAG_CUDA_OK(cudaFuncSetAttribute(attn_tc::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_tc::smem_bytes(512)));
-  DRAG_CUDA_OK(cudaFuncSetAttribute(attn_tc2::attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_tc2::smem_bytes(256)));   // the largest (3 stages of 2-tile items)
+  DRAG_CUDA_OK(cudaFuncSetAttribute(attn_tc::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_max));
+  DRAG_CUDA_OK(cudaFuncSetAttribute(attn_tc2::attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2_max));
   return DRAG_OK;
 }
 
