@@ -90,8 +90,11 @@ class DeviceMatrix:
         self.n_docs = len(offs) - 1
         self.doc_offsets = torch.tensor(offs, dtype=torch.int64, device=dev)
         self._ws = {}
-        # batched tensor-core path (built lazily on the first large query batch)
-        self.batch_min_queries = 8
+        # batched tensor-core path (built lazily on the first query batch that qualifies).  Crossover measured on
+        # B200, 384-d fp32, top-20 (scripts/batch_threshold_probe.py): over 1M rows the batch path takes 0.35 ms
+        # for any 1..16 queries against 0.55 / 1.10 / 2.19 ms for the float64 scan at 2 / 4 / 8 queries; over 100k
+        # rows 0.165 ms against 0.156 / 0.242 / 0.470 ms.  None = pick by index size; an int overrides.
+        self.batch_min_queries = None
         self.batch_min_rows = 8192
         self._batch_state = None
         self.last_batch_fallbacks = 0
@@ -142,8 +145,13 @@ class DeviceMatrix:
         self._batch_state = state
         return state
 
+    def _batch_threshold(self) -> int:
+        if self.batch_min_queries is not None:
+            return int(self.batch_min_queries)
+        return 2 if self.n_rows >= 262144 else (3 if self.n_rows >= 65536 else 8)
+
     def _use_batch(self, nq: int, k: int, metric_code: int) -> bool:
-        if nq < self.batch_min_queries or self.n_rows < self.batch_min_rows or k > BATCH_MAX_K:
+        if nq < self._batch_threshold() or self.n_rows < self.batch_min_rows or k > BATCH_MAX_K:
             return False
         state = self._batch_prepare()
         return bool(state["cos_ok"] if metric_code == METRIC_CODES["cosine_sim"] else state["ok"])
