@@ -422,10 +422,10 @@ def main() -> None:
         dist.init_process_group("nccl", device_id=device)
 
     from dial_rag_b200.embeddings.encoder import B200Encoder
-    from oracle import encoder as oenc  # weights generator only (shared with the oracle so both arms see the same tensors)
+    import synth_weights as synth  # neutral seeded-weights generator (the CPU arms draw the same tensors through the oracle)
 
     peaks = load_peaks()
-    weights = oenc.synth_weights(seed=0, style="hf_init")
+    weights = synth.synth_weights(seed=0, style="hf_init")
     chunks = args.chunks
     tokens = chunks * SEQ_LEN
     enc = B200Encoder(weights, device=local_rank, max_tokens=tokens)

@@ -10,13 +10,13 @@ import numpy as np
 import torch
 
 from dial_rag_b200.embeddings.encoder import B200Encoder
-from oracle import encoder as oenc
+import synth_weights
 
 n_seq = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 q_len = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 200
 dev = torch.device("cuda", 0)
-enc = B200Encoder(oenc.synth_weights(seed=0, style="hf_init"), device=0, max_tokens=n_seq * q_len)
+enc = B200Encoder(synth_weights.synth_weights(seed=0, style="hf_init"), device=0, max_tokens=n_seq * q_len)
 rng = np.random.default_rng(5)
 ids = rng.integers(1000, 30522, size=(n_seq, q_len), dtype=np.int32)
 ids[:, 0], ids[:, -1] = 101, 102
