@@ -16,7 +16,10 @@ limit).find/find_in_doc``, ``create_index_by_chunk/page``, ``pack_simple/multi_e
 
 from __future__ import annotations
 
+import os
 import threading
+import weakref
+from collections import OrderedDict
 from typing import Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -78,6 +81,78 @@ def _stack_documents(doc_indexes: Sequence[DocIndex]):
     return np.concatenate(mats), np.concatenate(ids), offsets
 
 
+
+class ResidentIndexCache:
+    """Device-resident indexes kept ACROSS requests.
+
+    The reference rebuilds its flat host arrays on every request (retrieval_chain.py:264-271 ->
+    ``from_doc_records``); with the matrix in HBM that would mean re-flattening and re-uploading it
+    per request.  The persisted per-document ``MultiEmbeddings`` objects, however, are the same Python
+    objects from request to request (the reference caches loaded ``DocumentRecord``s), so an index is
+    keyed by the IDENTITY of its source objects.  An entry holds only weak references to them: when a
+    source is collected or its length changes the entry is dropped, so a recycled ``id()`` can never
+    alias.  Least-recently-used entries are evicted beyond ``max_bytes`` (``DRAG_INDEX_CACHE_MB``,
+    default 16384) or ``max_entries``.
+    """
+
+    def __init__(self, max_entries: int = 16, max_bytes: Optional[int] = None):
+        if max_bytes is None:
+            max_bytes = int(os.environ.get("DRAG_INDEX_CACHE_MB", "16384")) << 20
+        self.max_entries, self.max_bytes = int(max_entries), int(max_bytes)
+        self._entries: "OrderedDict[tuple, tuple]" = OrderedDict()   # key -> (weakrefs, lengths, value, nbytes)
+        self._lock = threading.Lock()
+        self.hits = self.misses = 0
+
+    @staticmethod
+    def _key(sources: Sequence[object], extra: tuple) -> tuple:
+        return tuple(id(s) for s in sources) + ("|",) + tuple(extra)
+
+    def get(self, sources: Sequence[object], extra: tuple = ()):
+        key = self._key(sources, extra)
+        with self._lock:
+            entry = self._entries.get(key)
+            if entry is not None:
+                refs, lengths, value, _ = entry
+                alive = all(r() is s for r, s in zip(refs, sources, strict=True))
+                if alive and lengths == tuple(len(s) for s in sources):
+                    self._entries.move_to_end(key)
+                    self.hits += 1
+                    return value
+                del self._entries[key]
+            self.misses += 1
+            return None
+
+    def put(self, sources: Sequence[object], extra: tuple, value, nbytes: int) -> bool:
+        key = self._key(sources, extra)
+        try:
+            # a collected source drops the entry right away (frees the HBM it pins)
+            refs = tuple(weakref.ref(s, lambda _r, k=key: self._drop(k)) for s in sources)
+        except TypeError:
+            return False   # sources that cannot be weakly referenced are not cached
+        with self._lock:
+            self._entries[key] = (refs, tuple(len(s) for s in sources), value, int(nbytes))
+            self._entries.move_to_end(key)
+            while len(self._entries) > self.max_entries or (
+                len(self._entries) > 1 and sum(e[3] for e in self._entries.values()) > self.max_bytes
+            ):
+                self._entries.popitem(last=False)
+        return True
+
+    def _drop(self, key: tuple) -> None:
+        with self._lock:
+            self._entries.pop(key, None)
+
+    def clear(self) -> None:
+        with self._lock:
+            self._entries.clear()
+
+    def __len__(self) -> int:
+        return len(self._entries)
+
+
+RESIDENT_INDEXES = ResidentIndexCache()
+
+
 class EmbeddingsIndex:
     retrieval_type: RetrievalType
     doc_indexes: List[DocIndex]
@@ -96,12 +171,47 @@ class EmbeddingsIndex:
         self.retrieval_type = retrieval_type
         self.metric = metric
         self.limit = limit
-        self.doc_indexes = indexes
+        self._doc_indexes = indexes
+        self._sources: Optional[Sequence[object]] = None
         self._device_id = device
         self._storage = storage
         self._resident: Optional[DeviceMatrix] = None
         self._resident_empty = False
         self._lock = threading.Lock()
+
+    @property
+    def doc_indexes(self) -> List[DocIndex]:
+        """Per-document host arrays (the reference's ``indexes``); flattened lazily when the index came out of
+        the resident cache -- ``find`` does not need them."""
+        if self._doc_indexes is None:
+            self._doc_indexes = [create_index_by_chunk(src) for src in self._sources or ()]
+        return self._doc_indexes
+
+    @classmethod
+    def from_sources(
+        cls,
+        retrieval_type: RetrievalType,
+        sources: Sequence[object],
+        metric: Metric = Metric.SQEUCLIDEAN_DIST,
+        limit: int = 1,
+        device: Optional[int] = None,
+        storage: str = "f32",
+        cache: Optional["ResidentIndexCache"] = None,
+    ) -> "EmbeddingsIndex":
+        """An index over per-document ``MultiEmbeddings`` (one row per chunk, ``create_index_by_chunk``) whose
+        device-resident matrix is shared between requests through ``cache`` (default: the process-wide one)."""
+        cache = RESIDENT_INDEXES if cache is None else cache
+        sources = list(sources)
+        index = cls(retrieval_type, None, metric=metric, limit=limit, device=device, storage=storage)  # type: ignore[arg-type]
+        index._sources = sources
+        hit = cache.get(sources, (storage, device))
+        if hit is not None:
+            index._resident, index._resident_empty = hit
+            return index
+        matrix = index._matrix()   # flattens (doc_indexes) and uploads
+        nbytes = 0 if matrix is None else matrix.n_rows * matrix.dim * (4 if storage == "f32" else 2)
+        cache.put(sources, (storage, device), (matrix, matrix is None), nbytes)
+        return index
 
     # The matrix is uploaded on first use and then stays in HBM for the life of the
     # index object (the reference rebuilds host arrays per request, retrieval_chain.py:264-271).

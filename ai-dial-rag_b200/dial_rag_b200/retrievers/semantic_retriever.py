@@ -21,7 +21,6 @@ from dial_rag_b200.embeddings import embeddings as _emb
 from dial_rag_b200.records import Document, MultiEmbeddings, RetrievalType
 from dial_rag_b200.retrievers.embeddings_index import (
     EmbeddingsIndex,
-    create_index_by_chunk,
     pack_simple_embeddings,
 )
 
@@ -57,8 +56,10 @@ class SemanticRetriever(BaseRetriever):
 
     @classmethod
     def from_doc_records(cls, document_records: List[Any], k: int = 1) -> "SemanticRetriever":
-        indexes = [create_index_by_chunk(doc.embeddings_index) for doc in document_records if doc.embeddings_index]
-        return cls(index=EmbeddingsIndex(retrieval_type=RetrievalType.TEXT, indexes=indexes, limit=k))
+        # same documents as semantic_retriever.py:30-34; the flattened matrix stays in HBM between requests
+        # (keyed by the identity of the persisted per-document embeddings, see ResidentIndexCache)
+        sources = [doc.embeddings_index for doc in document_records if doc.embeddings_index]
+        return cls(index=EmbeddingsIndex.from_sources(RetrievalType.TEXT, sources, limit=k))
 
     def _find_relevant_documents(self, query_emb: np.ndarray) -> List[Document]:
         return self.index.find(query=query_emb)

@@ -96,6 +96,34 @@ def test_build_index_and_retrieve_matches_oracle(stack):
         assert len(set(got_pairs) & set(want_pairs)) >= 5, (q, got_pairs, want_pairs)
 
 
+def test_resident_index_is_shared_between_requests(stack):
+    """a retriever built again from the same document records (the reference does that per
+    request, retrieval_chain.py:264-271) reuses the matrix already in HBM; new records build a new one."""
+    emb, tok, w = stack
+    from dial_rag_b200.records import Chunk
+    from dial_rag_b200.retrievers.embeddings_index import RESIDENT_INDEXES
+    from dial_rag_b200.retrievers.semantic_retriever import SemanticRetriever
+
+    class Rec:
+        def __init__(self, embeddings_index):
+            self.embeddings_index = embeddings_index
+
+    RESIDENT_INDEXES.clear()
+    records = []
+    for d in (CHUNKS[:10], CHUNKS[10:25]):
+        chunks = [Chunk(text=t, metadata={"chunk_id": i}) for i, t in enumerate(d)]
+        records.append(Rec(asyncio.run(SemanticRetriever.build_index(chunks, io.StringIO()))))
+    first = SemanticRetriever.from_doc_records(records, k=5)
+    second = SemanticRetriever.from_doc_records(records, k=3)
+    assert first.index._matrix() is second.index._matrix() and len(RESIDENT_INDEXES) == 1
+    q = QUERIES[0]
+    assert second._get_relevant_documents(q) == first._get_relevant_documents(q)[:3]
+    assert [len(d) for d in second.index.doc_indexes] == [10, 15]          # host arrays still available on demand
+    other = SemanticRetriever.from_doc_records(records[::-1], k=3)          # another document order = other row ids
+    assert other.index._matrix() is not first.index._matrix() and len(RESIDENT_INDEXES) == 2
+    RESIDENT_INDEXES.clear()
+
+
 def test_embeddings_surface(stack):
     emb, tok, w = stack
     assert emb.EMBEDDING_LENGTH == 384
