@@ -80,6 +80,9 @@ _SIGNATURES = {
     "drag_debug_gemm": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int,
                                   C.c_float, C.c_float, _P]),
     "drag_debug_attention": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "drag_wordpiece_create": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_P)]),
+    "drag_wordpiece_destroy": (C.c_int, [_P]),
+    "drag_wordpiece_encode": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

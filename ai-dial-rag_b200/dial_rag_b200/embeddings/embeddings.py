@@ -85,14 +85,16 @@ class B200BgeEmbeddings(Embeddings):
 
     def embed_documents_numpy(self, texts: Sequence[str]) -> np.ndarray:
         prepared = [self.embed_instruction + t.replace("\n", " ") for t in texts]
-        return self.client.embed_token_lists(self.tokenizer.encode_batch(prepared))
+        if not prepared:
+            return np.zeros((0, EMBEDDING_LENGTH), dtype=np.float32)
+        return self.client.embed_packed(*self.tokenizer.encode_packed(prepared))
 
     def embed_documents(self, texts: List[str]) -> List[List[float]]:
         return self.embed_documents_numpy(texts).tolist()
 
     def embed_query(self, text: str) -> List[float]:
         prepared = self.query_instruction + text.replace("\n", " ")
-        return self.client.embed_token_lists(self.tokenizer.encode_batch([prepared]))[0].tolist()
+        return self.client.embed_packed(*self.tokenizer.encode_packed([prepared], n_threads=1))[0].tolist()
 
 
 _impl: Optional[B200BgeEmbeddings] = None

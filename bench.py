@@ -330,6 +330,55 @@ def bench_query_path(torch, device, weights, rows: int = 1_000_000, q_len: int =
     return out
 
 
+def bench_text_path(torch, device, weights, n_texts: int = 1024, steps: int = 5):
+    """raw text -> WordPiece (host, C++ fast path of the C-ABI library) -> packed ids -> CUDA encoder ->
+    host float32 embeddings, through the langchain-shaped ``embed_documents_numpy`` the indexing path calls.
+    Synthetic ASCII text (~256 tokens per chunk) over a synthetic 20k-word vocabulary."""
+    import tempfile
+
+    from dial_rag_b200.embeddings.embeddings import B200BgeEmbeddings
+    from dial_rag_b200.embeddings.tokenizer import WordPieceTokenizer
+
+    rng = np.random.default_rng(11)
+    syll = ["ka", "to", "mi", "ra", "ne", "su", "lo", "vi", "an", "er", "st", "on", "qu", "ph", "gl", "ice", "alp", "ber"]
+    words = sorted({"".join(rng.choice(syll, size=rng.integers(1, 4))) for _ in range(40000)})[:20000]
+    vocab = ["[PAD]"] + [f"[unused{i}]" for i in range(99)] + ["[UNK]", "[CLS]", "[SEP]", "[MASK]"]
+    vocab += list("abcdefghijklmnopqrstuvwxyz") + ["##" + c for c in "abcdefghijklmnopqrstuvwxyz"] + list(".,;:!?'-") + words
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "vocab.txt")
+        with open(path, "w") as f:
+            f.write("\n".join(dict.fromkeys(vocab)) + "\n")
+        tok = WordPieceTokenizer.from_vocab_file(path)
+        texts = []
+        for _ in range(n_texts):
+            ws = rng.choice(words, size=215)
+            texts.append(" ".join(w.capitalize() + ("," if i % 11 == 10 else "." if i % 17 == 16 else "") for i, w in enumerate(ws)))
+        ids, cu = tok.encode_packed(texts)
+        n_tokens = int(cu[-1])
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            tok.encode_packed(texts)
+        fast_s = (time.perf_counter() - t0) / steps
+        t0 = time.perf_counter()
+        tok.encode_batch(texts)
+        ref_s = time.perf_counter() - t0
+        impl = B200BgeEmbeddings(weights, tok, device=device.index, max_tokens=n_texts * 512)
+        for _ in range(2):
+            impl.embed_documents_numpy(texts)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = impl.embed_documents_numpy(texts)
+        e2e_s = (time.perf_counter() - t0) / steps
+        impl.client.close()
+    return {
+        "workload": f"{n_texts} synthetic ASCII chunks, {n_tokens / n_texts:.0f} tokens each, text -> tokenizer -> encoder -> host embeddings",
+        "tokens_per_s_wordpiece_native": n_tokens / fast_s, "tokens_per_s_wordpiece_reference": n_tokens / ref_s,
+        "host_threads": os.cpu_count(),
+        "chunks_per_s_text_to_embedding": n_texts / e2e_s,
+        "embedding_checksum": float(np.asarray(out, dtype=np.float64).sum()),
+    }
+
+
 def bench_search_sharded(torch, dist, device, rank, world, peaks, rows_per_gpu: int, n_queries: int, k: int, steps: int, warmup: int):
     """configs[3] shape: bf16 index row-sharded over the GPUs, replicated queries, one NCCL all-gather of
     the per-shard top-k candidates + drag_topk_merge on every rank."""
@@ -571,6 +620,7 @@ def main() -> None:
                 search["cpu_baseline"] = cpu_search_baseline()
             line["extra"]["search"] = search
             line["extra"]["query_path"] = bench_query_path(torch, device, weights)
+            line["extra"]["text_path"] = bench_text_path(torch, device, weights)
         except Exception as exc:  # noqa: BLE001 - the secondary metric must not lose the headline line
             line["extra"]["search"] = {"error": repr(exc)}
 

@@ -261,6 +261,27 @@ int drag_debug_tc_keys(int device, const void* d_shadow_bf16, int64_t n_rows, in
                        int metric, const double* d_queries, int n_queries, float* d_out_keys,
                        void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ *  Host-side WordPiece: the ASCII fast path of the uncased     *
+ *  BERT tokenizer the reference runs inside sentence-transformers            *
+ *  (aidial_rag/embeddings/embeddings.py:57-65 -> BertTokenizerFast).         *
+ * ------------------------------------------------------------------------- */
+typedef struct drag_wordpiece drag_wordpiece;
+
+/* vocab_path: BERT vocab.txt (id = line number; needs [UNK] [CLS] [SEP]). */
+int drag_wordpiece_create(const char* vocab_path, int lowercase, drag_wordpiece** out);
+int drag_wordpiece_destroy(drag_wordpiece* tk);
+
+/*
+ * Tokenise n_texts UTF-8 strings (text i = bytes[offsets[i] : offsets[i+1]]) on n_threads host threads
+ * (<= 0: all cores): clean-up, lower-casing, whitespace / punctuation split, greedy WordPiece,
+ * [CLS] ids[: max_len-2] [SEP].  out_ids: int32 [n_texts][max_len]; out_len[i] = number of ids of text i, or
+ * -1 when the text holds a non-ASCII byte or a literal special token and must go through the reference
+ * tokenizer (identical results by construction; the caller splices them in).  No GPU involved.
+ */
+int drag_wordpiece_encode(const drag_wordpiece* tk, const char* bytes, const int64_t* offsets, int n_texts,
+                          int max_len, int n_threads, int32_t* out_ids, int32_t* out_len);
+
 #ifdef __cplusplus
 }
 #endif
