@@ -22,14 +22,16 @@ Differences from the reference, all deliberate:
 
 from __future__ import annotations
 
+import asyncio
 import logging
 import os
 import threading
+from itertools import chain
 from typing import Iterable, List, Mapping, Optional, Sequence
 
 import numpy as np
 
-from dial_rag_b200.batched import batched_map_with_progress
+from dial_rag_b200.batched import TqdmProgressBar, batched_map_with_progress, chunked  # noqa: F401 (re-export)
 from dial_rag_b200.embeddings.detect_device import DeviceType, detect_device
 from dial_rag_b200.embeddings.encoder import BGE_SMALL, B200Encoder, EncoderShape, load_model_dir
 from dial_rag_b200.embeddings.tokenizer import WordPieceTokenizer
@@ -83,11 +85,18 @@ class B200BgeEmbeddings(Embeddings):
     def from_model_dir(cls, path: str, device: int = 0, **kw) -> "B200BgeEmbeddings":
         return cls(load_model_dir(path), WordPieceTokenizer.from_model_dir(path), device=device, **kw)
 
-    def embed_documents_numpy(self, texts: Sequence[str]) -> np.ndarray:
-        prepared = [self.embed_instruction + t.replace("\n", " ") for t in texts]
-        if not prepared:
+    def tokenize_documents(self, texts: Sequence[str]):
+        """Host half of ``embed_documents``: text preparation + WordPiece -> packed ``(ids, cu_seqlens)``."""
+        return self.tokenizer.encode_packed([self.embed_instruction + t.replace("\n", " ") for t in texts])
+
+    def embed_packed_numpy(self, ids: np.ndarray, cu_seqlens: np.ndarray) -> np.ndarray:
+        """Device half: packed ids -> float32 ``[n, 384]`` on the host."""
+        if len(cu_seqlens) <= 1:
             return np.zeros((0, EMBEDDING_LENGTH), dtype=np.float32)
-        return self.client.embed_packed(*self.tokenizer.encode_packed(prepared))
+        return self.client.embed_packed(ids, cu_seqlens)
+
+    def embed_documents_numpy(self, texts: Sequence[str]) -> np.ndarray:
+        return self.embed_packed_numpy(*self.tokenize_documents(texts))
 
     def embed_documents(self, texts: List[str]) -> List[List[float]]:
         return self.embed_documents_numpy(texts).tolist()
@@ -152,6 +161,19 @@ bge_embedding = AsyncEmbeddings()
 
 
 async def build_embeddings(texts: Iterable[str], stageio):
-    """Embed ``texts`` in order, batch by batch, with progress lines (embeddings.py:102-108)."""
-    return await batched_map_with_progress(
-        texts, bge_embedding.aembed_documents_numpy, EMBEDDINGS_BATCH_SIZE, file=stageio)
+    """Embed ``texts`` in order, batch by batch, with progress lines (embeddings.py:102-108).
+
+    Same contract as the reference (ordered results, ONE batch at a time on the indexing-embeddings worker,
+    tqdm keep-alive lines); the only addition is that batch i+1 is tokenised on the loop's default executor
+    while batch i is on the GPU, so the host half never leaves the device idle."""
+    impl = bge_embedding_impl()
+    loop = asyncio.get_running_loop()
+    batches = list(chunked(texts, EMBEDDINGS_BATCH_SIZE))
+    results = []
+    ahead = loop.run_in_executor(None, impl.tokenize_documents, batches[0]) if batches else None
+    for i, _ in enumerate(TqdmProgressBar(iterable=batches, file=stageio)):
+        ids, cu = await ahead
+        ahead = loop.run_in_executor(None, impl.tokenize_documents, batches[i + 1]) if i + 1 < len(batches) else None
+        matrix = await run_in_indexing_embeddings_pool(impl.embed_packed_numpy, ids, cu)   # strictly one batch in flight
+        results.append(list(matrix))  # float32 row views, shape (384,)
+    return chain.from_iterable(results)

@@ -369,12 +369,28 @@ def bench_text_path(torch, device, weights, n_texts: int = 1024, steps: int = 5)
         for _ in range(steps):
             out = impl.embed_documents_numpy(texts)
         e2e_s = (time.perf_counter() - t0) / steps
+        # ... and through build_embeddings (the indexing entry point: batches of EMBEDDINGS_BATCH_SIZE, batch i+1
+        # tokenised while batch i is on the GPU)
+        import asyncio
+        import io
+
+        from dial_rag_b200.embeddings import embeddings as emb
+
+        emb.configure(impl)
+        many = texts * 8
+        asyncio.run(emb.build_embeddings(texts, io.StringIO()))
+        t0 = time.perf_counter()
+        rows = list(asyncio.run(emb.build_embeddings(many, io.StringIO())))
+        build_s = time.perf_counter() - t0
+        assert len(rows) == len(many)
+        emb.configure(None)
         impl.client.close()
     return {
         "workload": f"{n_texts} synthetic ASCII chunks, {n_tokens / n_texts:.0f} tokens each, text -> tokenizer -> encoder -> host embeddings",
         "tokens_per_s_wordpiece_native": n_tokens / fast_s, "tokens_per_s_wordpiece_reference": n_tokens / ref_s,
         "host_threads": os.cpu_count(),
         "chunks_per_s_text_to_embedding": n_texts / e2e_s,
+        "chunks_per_s_build_embeddings": len(many) / build_s,
         "embedding_checksum": float(np.asarray(out, dtype=np.float64).sum()),
     }
 
