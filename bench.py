@@ -220,7 +220,10 @@ def search_roofline(peaks, n_queries: int, rows: int, ms: float, elem_bytes: int
     bytes_per_pass = rows * HIDDEN * elem_bytes
     roof = {"bound": "hbm", "achieved": passes * bytes_per_pass / (ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"],
             "unit": "GB/s", "frac": passes * bytes_per_pass / (ms / 1e3) / 1e9 / peaks["hbm_gbs"],
-            "note": "algorithmic bytes = one read of the matrix per pass of <=4 queries"}
+            # ncu --set full of scan_ring_kernel: dram__bytes_read.sum = 1.0016 x N*D*4 (profiles/r01_f_scan_ring_ncu.txt)
+            "traffic": 1.0016 * passes * bytes_per_pass,
+            "note": "algorithmic bytes = one read of the matrix per pass of <=4 queries; the time includes the query "
+                    "preparation and list-merge kernels of the call"}
     return roof, "float64 scan (drag_topk)", passes
 
 
