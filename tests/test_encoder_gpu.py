@@ -193,6 +193,32 @@ def test_batch_composition_invariance(model):
     assert np.array_equal(rev[::-1], whole)
 
 
+def test_more_sequences_than_one_grid_dimension():
+    """70 000 two-token sequences in ONE forward: the attention launch is cut at gridDim.y = 65 535 and the
+    halves must meet seamlessly (compared with the same sequences embedded in two batches)."""
+    import synth_weights
+    from dial_rag_b200.embeddings.encoder import B200Encoder
+
+    n = 70_000
+    rng = np.random.default_rng(3)
+    ids = rng.integers(1000, 30522, size=(n, 2), dtype=np.int32)
+    ids[:, 0] = 101
+    cu = np.arange(0, 2 * n + 1, 2, dtype=np.int32)
+    enc = B200Encoder(synth_weights.synth_weights(seed=0, style="hf_init"), device=0, max_tokens=2 * n)
+    try:
+        whole = enc.embed_packed(ids.reshape(-1), cu)
+        half = n // 2
+        a = enc.embed_packed(ids[:half].reshape(-1), cu[: half + 1])
+        b = enc.embed_packed(ids[half:].reshape(-1), cu[: n - half + 1])
+    finally:
+        enc.close()
+    assert np.isfinite(whole).all()
+    assert np.array_equal(whole[:half], a) and np.array_equal(whole[half:], b)
+    # identical inputs give identical rows wherever they sit in the batch
+    same = np.flatnonzero((ids[:, 1] == ids[0, 1]))
+    assert all(np.array_equal(whole[i], whole[0]) for i in same)
+
+
 def test_config2_shape_vs_oracle(model):
     """BASELINE config 2 shape (256-token chunks, all real tokens): oracle on a 64-chunk prefix."""
     style, w, enc = model
