@@ -194,6 +194,11 @@ def test_bf16_storage_recall_and_exactness():
         np.testing.assert_allclose(dist[i], want_d, rtol=1e-11, atol=1e-12)
         full = -(m.astype(np.float64) @ q[i])
         assert np.max(np.abs(full[rows[i]] - dist[i])) <= 2.0**-8
+    # one query at a time goes through the shared-memory ring scan on the bf16 rows (the four above took the
+    # tensor-core candidate pass + float64 re-rank): same float64 arithmetic, bit-identical answers
+    for i in range(2):
+        d1, r1, _ = dm.topk(q[i:i + 1], 100, "inner_product")
+        assert np.array_equal(r1[0], rows[i]) and np.array_equal(d1[0], dist[i])
 
 
 def test_sharded_merge_equals_single_scan():
