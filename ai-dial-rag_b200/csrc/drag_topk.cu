@@ -899,13 +899,19 @@ static int launch_scan_t(const ScanArgs& a, const Plan& p, bool vec_ok, cudaStre
     DRAG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RING_SMEM)); \
     kern<<<grid, dim3((RING_WARPS + 1) * 32), smem, st>>>(a, n_stages, (unsigned)lists_bytes);      \
   }
-  if (QB == 1 && vec_ok && nch <= 4 && n_stages >= 2 && !ring_off && ((uintptr_t)a.mat & 15) == 0) {
-    switch (nch) {
-      case 1: DRAG_LAUNCH_RING(1) break;
-      case 2: DRAG_LAUNCH_RING(2) break;
-      case 3: DRAG_LAUNCH_RING(3) break;
-      default: DRAG_LAUNCH_RING(4) break;
+  bool ring_done = false;
+  if constexpr (QB == 1) {   // (only the single-query ring kernels are instantiated)
+    if (vec_ok && nch <= 4 && n_stages >= 2 && !ring_off && ((uintptr_t)a.mat & 15) == 0) {
+      switch (nch) {
+        case 1: DRAG_LAUNCH_RING(1) break;
+        case 2: DRAG_LAUNCH_RING(2) break;
+        case 3: DRAG_LAUNCH_RING(3) break;
+        default: DRAG_LAUNCH_RING(4) break;
+      }
+      ring_done = true;
     }
+  }
+  if (ring_done) {
   } else if (vec_ok && nch <= 4) {
     switch (nch) {
       case 1: DRAG_LAUNCH_VEC(1) break;
