@@ -72,8 +72,10 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "memory");
 }
 
-__device__ __forceinline__ void softmax_barrier() {
-  asm volatile("bar.sync 1, %0;" ::"n"(SOFTMAX_WARPS * 32) : "memory");
+// The four threads of a query row sit in the four warps that share a TMEM lane quarter (w, w+4, w+8, w+12):
+// those 128 threads synchronise among themselves (named barrier 1 + quarter), not the whole CTA.
+__device__ __forceinline__ void softmax_barrier(int quarter) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "n"(SOFTMAX_WARPS * 32 / 4) : "memory");
 }
 
 // Walks the CTA's tiles in a fixed order: items blockIdx.x + i * gridDim.x, their query tiles, and per
@@ -401,7 +403,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(p_full);
-      softmax_barrier();         // one per tile: publishes this tile's (m_u, l_u)
+      softmax_barrier(warp & 3); // one per tile: publishes this tile's (m_u, l_u) to the row's other three threads
       pend = true; pend_t = t; pend_first = w.job_first; pend_last = w.job_last;
       pend_units = (n_keys + UNIT - 1) / UNIT;
       pend_qrow = w.qt * TILE + row; pend_S = w.S; pend_tok0 = w.tok0; pend_head = w.item % heads;
