@@ -21,6 +21,7 @@
 #include "drag_attention.cuh"
 #include "drag_attention_tc.cuh"
 #include "drag_attention_tc2.cuh"
+#include "drag_attention_tc3.cuh"
 #include "drag_common.cuh"
 #include "drag_gemm.cuh"
 
@@ -109,6 +110,7 @@ __device__ __forceinline__ void apply_ln12(float (&v)[12], int lane, const float
 
 // out[s] = normalize(normalize(LN(x_raw[cu[s]])))  -- final LayerNorm of the CLS row, CLS pooling and
 // the two F.normalize(p=2, eps=1e-12)
+// (cu_seqlens == nullptr: the rows are already compact, row = sequence -- the CLS-only last layer)
 __global__ void __launch_bounds__(256)
 pool_normalize_kernel(const bf16* __restrict__ x, const float2* __restrict__ stats, const float* __restrict__ gamma,
                       const float* __restrict__ beta, float eps, const int* __restrict__ cu_seqlens, int n_seq,
@@ -116,7 +118,7 @@ pool_normalize_kernel(const bf16* __restrict__ x, const float2* __restrict__ sta
   const int seq = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (seq >= n_seq) return;
-  const size_t row = (size_t)cu_seqlens[seq];
+  const size_t row = cu_seqlens ? (size_t)cu_seqlens[seq] : (size_t)seq;
   float v[12];
   load_row12(x + row * HIDDEN, lane, v);
   apply_ln12(v, lane, stats, row, gamma, beta, eps);
@@ -132,6 +134,83 @@ pool_normalize_kernel(const bf16* __restrict__ x, const float2* __restrict__ sta
   for (int c = 0; c < 3; ++c)
     *reinterpret_cast<float4*>(out + (size_t)seq * HIDDEN + c * 128 + lane * 4) =
         make_float4(v[c * 4] * inv, v[c * 4 + 1] * inv, v[c * 4 + 2] * inv, v[c * 4 + 3] * inv);
+}
+
+// Last layer, CLS-only: only the [CLS] row of every sequence is pooled, so after the last QKV
+// projection nothing but those rows is needed.  One warp per (sequence, head): softmax(q_cls K^T / sqrt(32)) V for the
+// CLS query alone (fp32 arithmetic on the bf16 Q/K/V, exact single-pass softmax) -> ctx_c[seq]; the block also gathers
+// the raw CLS row of the residual stream and its statistics into compact rows (row = sequence), which the M = n_seq
+// out-projection / FFN GEMMs of the last layer then work on.  Block = heads warps: together they read whole 768-byte
+// K and V rows of the sequence's tokens.
+__global__ void __launch_bounds__(384)
+cls_attention_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ x, const float2* __restrict__ stats_x,
+                     const int* __restrict__ cu_seqlens, int heads, float scale_log2, bf16* __restrict__ ctx_c,
+                     bf16* __restrict__ res_c, float2* __restrict__ stats_c) {
+  const int seq = blockIdx.x;
+  const int head = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hidden = heads * HEAD_DIM, ld = 3 * hidden;
+  const int tok0 = cu_seqlens[seq];
+  const int S = cu_seqlens[seq + 1] - tok0;
+  // gather: raw CLS row + statistics
+  res_c[(size_t)seq * hidden + head * HEAD_DIM + lane] = x[(size_t)tok0 * hidden + head * HEAD_DIM + lane];
+  if (head == 0 && lane < PARTS) stats_c[(size_t)seq * PARTS + lane] = stats_x[(size_t)tok0 * PARTS + lane];
+  auto unpack8 = [](const uint4& v, float (&f)[8]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  };
+  float q[HEAD_DIM];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(qkv + (size_t)tok0 * ld + head * HEAD_DIM);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { float f[8]; unpack8(__ldg(qp + c), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[c * 8 + i] = f[i] * scale_log2; }
+  }
+  constexpr int MAX_PER_LANE = 16;   // max_pos 512 / 32 lanes
+  float sc[MAX_PER_LANE];
+  float m = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < MAX_PER_LANE; ++t) {
+    const int key = t * 32 + lane;
+    sc[t] = -INFINITY;
+    if (key < S) {
+      const uint4* kp = reinterpret_cast<const uint4*>(qkv + (size_t)(tok0 + key) * ld + hidden + head * HEAD_DIM);
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { float f[8]; unpack8(__ldg(kp + c), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dot = fmaf(q[c * 8 + i], f[i], dot); }
+      sc[t] = dot;
+      m = fmaxf(m, dot);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float l = 0.f, acc[HEAD_DIM];
+#pragma unroll
+  for (int i = 0; i < HEAD_DIM; ++i) acc[i] = 0.f;
+#pragma unroll
+  for (int t = 0; t < MAX_PER_LANE; ++t) {
+    const int key = t * 32 + lane;
+    if (key < S) {
+      const float p = exp2f(sc[t] - m);
+      l += p;
+      const uint4* vp = reinterpret_cast<const uint4*>(qkv + (size_t)(tok0 + key) * ld + 2 * hidden + head * HEAD_DIM);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { float f[8]; unpack8(__ldg(vp + c), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[c * 8 + i] = fmaf(p, f[i], acc[c * 8 + i]); }
+    }
+  }
+  l = warp_sum(l);
+  float mine = 0.f;
+#pragma unroll
+  for (int i = 0; i < HEAD_DIM; ++i) {
+    const float v = warp_sum(acc[i]);
+    if (lane == i) mine = v;
+  }
+  ctx_c[(size_t)seq * hidden + head * HEAD_DIM + lane] = __float2bfloat16_rn(mine / l);
 }
 
 // debug tap: hidden[t] = LN(x_raw[t]) as fp32 (what HF's BertModel exposes as a layer output)
@@ -188,26 +267,18 @@ struct Layer {
 using namespace drag;
 using namespace drag::enc;
 
-struct drag_encoder {
-  drag_bert_shape shape;
-  int device = 0;
-  int sms = 0;
+// Activation workspace + host-buffer staging of one forward in flight.  An encoder owns two: the BULK workspace
+// (max_tokens: indexing batches) and a small QUERY workspace with its own high-priority stream, so that a query
+// embedding never queues behind an indexing forward -- neither on the host lock nor in the stream (the reference keeps
+// two thread pools for exactly that, aidial_rag/resources/cpu_pools.py:50-59).
+struct Workspace {
   int64_t max_tokens = 0;  // padded to a multiple of 128
-  std::mutex lock;
-  std::vector<void*> allocs;
-  float *word = nullptr, *pos = nullptr, *type0 = nullptr, *emb_g = nullptr, *emb_b = nullptr;
-  std::vector<Layer> layers;
   // activations (bf16): x / y are RAW (pre-LayerNorm) hidden states with their row statistics
   bf16 *x = nullptr, *y = nullptr, *qkv = nullptr, *ctx = nullptr, *h = nullptr;
   float2 *stats_x = nullptr, *stats_y = nullptr;  // [T][PARTS] partial (sum, sum^2)
   CUtensorMap tm_x, tm_y, tm_ctx, tm_h;           // A-operand loads (128 x 64 boxes)
   CUtensorMap ts_x, ts_y, ts_qkv, ts_h;           // epilogue stores (32 x 64 boxes)
   CUtensorMap tm_qkv_heads;                       // attention loads: 128 tokens x one head (32 columns)
-  // cta_group::2 (CTA-pair) GEMMs: bit 0 QKV, 1 out-proj, 2 FFN-up, 3 FFN-down; bit 4: weights-stationary FFN-up.  Measured on B200 (same run,
-  // 262144 tokens): QKV 0.255 vs 0.267 ms, FFN-up 0.365 vs 0.375, FFN-down 0.339 vs 0.397 in favour of pairs;
-  // the out-projection (N = K = 384, epilogue-bound) 0.178 vs 0.202 in favour of single CTAs.  DRAG_GEMM_PAIRS=<mask>.
-  int gemm_pairs = 15;
-  int attention_variant = 0;                      // 0 = mma.sync kernel (default: faster today), 1 = tcgen05 kernel (DRAG_ATTENTION=tc)
   // host-buffer path
   cudaStream_t stream = nullptr;
   int32_t *d_ids = nullptr, *d_cu = nullptr;
@@ -215,21 +286,43 @@ struct drag_encoder {
   int32_t *p_ids = nullptr, *p_cu = nullptr;
   float* p_out = nullptr;
   int64_t out_cap = 0;
-  // optional per-kernel-class timing (bench.py roofline): event pairs recorded around launches
+  std::mutex lock;            // host threads enqueue one forward at a time per workspace
+  cudaEvent_t done = nullptr; // recorded behind every forward: the next one (on whatever stream) waits for it
+  bool used = false;
+};
+
+constexpr int64_t QUERY_WORKSPACE_TOKENS = 8192;   // 16 queries of 512 tokens
+
+struct drag_encoder {
+  drag_bert_shape shape;
+  int device = 0;
+  int sms = 0;
+  int64_t max_tokens = 0;  // padded to a multiple of 128
+  std::vector<void*> allocs;
+  float *word = nullptr, *pos = nullptr, *type0 = nullptr, *emb_g = nullptr, *emb_b = nullptr;
+  std::vector<Layer> layers;
+  Workspace ws[2];         // 0 = bulk, 1 = query
+  // cta_group::2 (CTA-pair) GEMMs: bit 0 QKV, 1 out-proj, 2 FFN-up, 3 FFN-down; bit 4: weights-stationary FFN-up.  Measured on B200 (same run,
+  // 262144 tokens): QKV 0.255 vs 0.267 ms, FFN-up 0.365 vs 0.375, FFN-down 0.339 vs 0.397 in favour of pairs;
+  // the out-projection (N = K = 384, epilogue-bound) 0.178 vs 0.202 in favour of single CTAs.  DRAG_GEMM_PAIRS=<mask>.
+  int gemm_pairs = 15;
+  int attention_variant = 0;                      // 0 = mma.sync kernel, 3 / 4 = tcgen05 kernel (DRAG_ATTENTION)
+  bool cls_only = true;                           // last layer on the [CLS] rows only (DRAG_CLS_ONLY=0: all rows)
+  // optional per-kernel-class timing (bench.py roofline): event pairs recorded around the launches of the bulk workspace
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;  // start/stop pairs
   std::vector<int> prof_class;
   size_t prof_used = 0;
 };
 
-enum KernelClass { KC_EMBED = 0, KC_GEMM_QKV, KC_ATTENTION, KC_GEMM_OUT_LN, KC_GEMM_UP_GELU, KC_GEMM_DOWN_LN, KC_POOL, KC_COUNT };
+enum KernelClass { KC_EMBED = 0, KC_GEMM_QKV, KC_ATTENTION, KC_GEMM_OUT_LN, KC_GEMM_UP_GELU, KC_GEMM_DOWN_LN, KC_POOL, KC_CLS_TAIL, KC_COUNT };
 
 struct ProfScope {
   drag_encoder* e;
   cudaStream_t st;
   cudaEvent_t stop = nullptr;
-  ProfScope(drag_encoder* enc, int klass, cudaStream_t s) : e(enc), st(s) {
-    if (!e->profiling || e->prof_used + 2 > e->prof_events.size()) return;
+  ProfScope(drag_encoder* enc, const Workspace& ws, int klass, cudaStream_t s) : e(enc), st(s) {
+    if (!e->profiling || &ws != &e->ws[0] || e->prof_used + 2 > e->prof_events.size()) return;
     cudaEventRecord(e->prof_events[e->prof_used], st);
     stop = e->prof_events[e->prof_used + 1];
     e->prof_class.push_back(klass);
@@ -341,7 +434,27 @@ int launch_gemm(const drag_encoder* e, const CUtensorMap& ta, const CUtensorMap&
 int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* qkv, bf16* ctx, const int32_t* d_cu,
                      int n_seq, int max_len, int heads, cudaStream_t st) {
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)HEAD_DIM);
-  if (variant == 2) {
+  if (variant == 3 || variant == 4) {
+    // tcgen05, two out-of-phase softmax groups (drag_attention_tc3.cuh); variant 4 double-buffers P
+    const int p_bufs = variant == 4 ? 2 : 1;
+    int sms = 148;
+    {
+      int dev = 0;
+      if (cudaGetDevice(&dev) == cudaSuccess && sm_count(dev) > 0) sms = sm_count(dev);
+    }
+    const int items = heads * n_seq;
+    const int split = attn3::pick_split(items, max_len, sms);
+    const int units = items * split;
+    const size_t smem = attn3::smem_bytes(max_len, p_bufs);
+    const int max_tiles = (max_len + attn3::TILE - 1) / attn3::TILE;
+    const int grid = units < sms ? units : sms;
+    if (p_bufs == 2)
+      attn3::attention_tc3_kernel<2><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles,
+                                                                        attn3::unit_stages(max_len, 2), split, scale_log2);
+    else
+      attn3::attention_tc3_kernel<1><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles,
+                                                                        attn3::unit_stages(max_len, 1), split, scale_log2);
+  } else if (variant == 2) {
     const size_t smem = attn_tc2::smem_bytes(max_len);
     const int items = heads * n_seq;
     int sms = 148;
@@ -378,11 +491,15 @@ int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* q
 
 int attention_set_attributes() {
   // the shared-memory need is not monotonic in the sequence length (fewer stages for longer items): take the maximum
-  size_t tc_max = 0, tc2_max = 0;
+  size_t tc_max = 0, tc2_max = 0, tc3_max[2] = {0, 0};
   for (int len = 128; len <= 512; len += 128) {
     tc_max = attn_tc::smem_bytes(len) > tc_max ? attn_tc::smem_bytes(len) : tc_max;
     tc2_max = attn_tc2::smem_bytes(len) > tc2_max ? attn_tc2::smem_bytes(len) : tc2_max;
+    for (int pb = 1; pb <= 2; ++pb)
+      tc3_max[pb - 1] = attn3::smem_bytes(len, pb) > tc3_max[pb - 1] ? attn3::smem_bytes(len, pb) : tc3_max[pb - 1];
   }
+  DRAG_CUDA_OK(cudaFuncSetAttribute(attn3::attention_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3_max[0]));
+  DRAG_CUDA_OK(cudaFuncSetAttribute(attn3::attention_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3_max[1]));
   DRAG_CUDA_OK(cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::smem_bytes(512)));
   DRAG_CUDA_OK(cudaFuncSetAttribute(attn_tc::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_max));
   DRAG_CUDA_OK(cudaFuncSetAttribute(attn_tc2::attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2_max));
@@ -401,7 +518,7 @@ int attention_set_attributes() {
 #define DRAG_GEMM2_RES launch_gemm<RES_BLOCK_N_PAIR, gemm::EPI_RES, 12, 4, 2>
 #define DRAG_GEMM2_RES_WS launch_gemm<RES_BLOCK_N_PAIR, gemm::EPI_RES, 12, 3, 2, true>
 
-int forward_impl(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu, const int32_t* h_cu, int n_seq,
+int forward_impl(drag_encoder* e, Workspace& ws, const int32_t* d_ids, const int32_t* d_cu, const int32_t* h_cu, int n_seq,
                  float* d_out, int stop_after_layer, float* d_hidden, cudaStream_t st) {
   DRAG_REQUIRE(e && d_ids && d_cu && h_cu, "drag_encoder_forward: null pointer");
   DRAG_REQUIRE(n_seq >= 0, "drag_encoder_forward: n_seq < 0");
@@ -414,76 +531,95 @@ int forward_impl(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu, con
     if (len > max_len) max_len = len;
   }
   const int total = h_cu[n_seq];
-  DRAG_REQUIRE((int64_t)total <= e->max_tokens, "drag_encoder_forward: %d tokens exceed max_tokens=%lld", total, (long long)e->max_tokens);
+  DRAG_REQUIRE((int64_t)total <= ws.max_tokens, "drag_encoder_forward: %d tokens exceed max_tokens=%lld", total, (long long)ws.max_tokens);
   const drag_bert_shape& sh = e->shape;
 
   const bool tap = d_hidden != nullptr;
   {
-    ProfScope prof(e, KC_EMBED, st);
+    ProfScope prof(e, ws, KC_EMBED, st);
     const int warps_per_block = 8;
     const int blocks = (total + warps_per_block - 1) / warps_per_block;
     embed_kernel<<<blocks, warps_per_block * 32, 0, st>>>(d_ids, d_cu, n_seq, total, e->word, e->pos, e->type0, sh.vocab,
-                                                         e->x, e->stats_x);
+                                                         ws.x, ws.stats_x);
     DRAG_CUDA_OK(cudaGetLastError());
   }
   const int n_layers = (tap && stop_after_layer < sh.layers) ? stop_after_layer : sh.layers;
+  // the pooled output needs the [CLS] rows of the last layer only (the debug tap wants every row)
+  const bool cls_tail = e->cls_only && !tap && d_out && n_layers == sh.layers && n_layers >= 1;
   for (int l = 0; l < n_layers; ++l) {
     const Layer& L = e->layers[l];
+    const bool last_cls = cls_tail && l == n_layers - 1;
     gemm::GemmParams p{};
     p.M = total;
     p.ln_eps = sh.ln_eps;
     p.inv_width = 1.0f / HIDDEN;
     int rc;
     // QKV projection of LN_in(x): qkv = rstd*(x_raw . (gamma (.) Wqkv)^T - mu*c) + d
-    p.N = 3 * HIDDEN; p.K = HIDDEN; p.colc = L.qkv_c; p.cold = L.qkv_d; p.in_stats = e->stats_x;
+    p.N = 3 * HIDDEN; p.K = HIDDEN; p.colc = L.qkv_c; p.cold = L.qkv_d; p.in_stats = ws.stats_x;
     {
-      ProfScope prof(e, KC_GEMM_QKV, st);
-      rc = (e->gemm_pairs & 1) ? DRAG_GEMM2_QKV(e, e->tm_x, L.tp_qkv, e->ts_qkv, e->ts_qkv, p, st) : DRAG_GEMM_QKV(e, e->tm_x, L.tm_qkv, e->ts_qkv, e->ts_qkv, p, st);
+      ProfScope prof(e, ws, KC_GEMM_QKV, st);
+      rc = (e->gemm_pairs & 1) ? DRAG_GEMM2_QKV(e, ws.tm_x, L.tp_qkv, ws.ts_qkv, ws.ts_qkv, p, st) : DRAG_GEMM_QKV(e, ws.tm_x, L.tm_qkv, ws.ts_qkv, ws.ts_qkv, p, st);
     }
     if (rc) return rc;
-    // attention
+    // From here on the last layer works on COMPACT rows (row = sequence) when only the pooled output is wanted:
+    // src / dst swap roles (the full-size buffers of the previous layer are dead).
+    bf16 *res = ws.x, *mid = ws.y;
+    float2 *res_stats = ws.stats_x, *mid_stats = ws.stats_y;
+    const CUtensorMap *tm_res = &ws.tm_x, *ts_res = &ws.ts_x, *tm_mid = &ws.tm_y, *ts_mid = &ws.ts_y;
+    if (last_cls) {
+      ProfScope prof(e, ws, KC_CLS_TAIL, st);
+      const float scale_log2 = 1.4426950408889634f / sqrtf((float)HEAD_DIM);
+      cls_attention_kernel<<<n_seq, sh.heads * 32, 0, st>>>(ws.qkv, ws.x, ws.stats_x, d_cu, sh.heads, scale_log2, ws.ctx, ws.y, ws.stats_y);
+      DRAG_CUDA_OK(cudaGetLastError());
+      res = ws.y; mid = ws.x; res_stats = ws.stats_y; mid_stats = ws.stats_x;
+      tm_res = &ws.tm_y; ts_res = &ws.ts_y; tm_mid = &ws.tm_x; ts_mid = &ws.ts_x;
+      p.M = n_seq;
+    } else {
+      ProfScope prof(e, ws, KC_ATTENTION, st);
+      rc = launch_attention(e->attention_variant, ws.tm_qkv_heads, ws.qkv, ws.ctx, d_cu, n_seq, max_len, sh.heads, st);
+      if (rc) return rc;
+    }
+    // mid_raw = ctx . Wo^T + b_o + LN_in(res_raw)   (+ row statistics of mid_raw)
+    p.N = HIDDEN; p.K = HIDDEN; p.colc = nullptr; p.cold = L.o_cold; p.gamma = L.o_gamma; p.in_stats = res_stats;
+    p.residual = res; p.out_stats = mid_stats;
     {
-      ProfScope prof(e, KC_ATTENTION, st);
-      rc = launch_attention(e->attention_variant, e->tm_qkv_heads, e->qkv, e->ctx, d_cu, n_seq, max_len, sh.heads, st);
+      ProfScope prof(e, ws, last_cls ? KC_CLS_TAIL : KC_GEMM_OUT_LN, st);
+      rc = (e->gemm_pairs & 2) ? DRAG_GEMM2_RES_WS(e, ws.tm_ctx, L.tp_o, *ts_mid, *ts_res, p, st) : DRAG_GEMM_RES(e, ws.tm_ctx, L.tm_o, *ts_mid, *ts_res, p, st);
     }
     if (rc) return rc;
-    // y_raw = ctx . Wo^T + b_o + LN_in(x_raw)   (+ row statistics of y_raw)
-    p.N = HIDDEN; p.K = HIDDEN; p.colc = nullptr; p.cold = L.o_cold; p.gamma = L.o_gamma; p.in_stats = e->stats_x;
-    p.residual = e->x; p.out_stats = e->stats_y;
-    {
-      ProfScope prof(e, KC_GEMM_OUT_LN, st);
-      rc = (e->gemm_pairs & 2) ? DRAG_GEMM2_RES_WS(e, e->tm_ctx, L.tp_o, e->ts_y, e->ts_x, p, st) : DRAG_GEMM_RES(e, e->tm_ctx, L.tm_o, e->ts_y, e->ts_x, p, st);
-    }
-    if (rc) return rc;
-    // h = gelu(LN_1(y) . W1^T + b_1)
-    p.N = sh.inter; p.K = HIDDEN; p.colc = L.up_c; p.cold = L.up_d; p.gamma = nullptr; p.in_stats = e->stats_y;
+    // h = gelu(LN_1(mid) . W1^T + b_1)
+    p.N = sh.inter; p.K = HIDDEN; p.colc = L.up_c; p.cold = L.up_d; p.gamma = nullptr; p.in_stats = mid_stats;
     p.residual = nullptr; p.out_stats = nullptr;
     {
-      ProfScope prof(e, KC_GEMM_UP_GELU, st);
-      rc = (e->gemm_pairs & 16) ? DRAG_GEMM2_UP_WS(e, e->tm_y, L.tp_up, e->ts_h, e->ts_h, p, st)
-           : (e->gemm_pairs & 4) ? DRAG_GEMM2_UP(e, e->tm_y, L.tp_up, e->ts_h, e->ts_h, p, st) : DRAG_GEMM_UP(e, e->tm_y, L.tm_up, e->ts_h, e->ts_h, p, st);
+      ProfScope prof(e, ws, last_cls ? KC_CLS_TAIL : KC_GEMM_UP_GELU, st);
+      rc = (e->gemm_pairs & 16) ? DRAG_GEMM2_UP_WS(e, *tm_mid, L.tp_up, ws.ts_h, ws.ts_h, p, st)
+           : (e->gemm_pairs & 4) ? DRAG_GEMM2_UP(e, *tm_mid, L.tp_up, ws.ts_h, ws.ts_h, p, st) : DRAG_GEMM_UP(e, *tm_mid, L.tm_up, ws.ts_h, ws.ts_h, p, st);
     }
     if (rc) return rc;
-    // x_raw = h . W2^T + b_2 + LN_1(y_raw)   (+ row statistics of x_raw); LN_2 is applied by the consumers
-    p.N = HIDDEN; p.K = sh.inter; p.colc = nullptr; p.cold = L.down_cold; p.gamma = L.down_gamma; p.in_stats = e->stats_y;
-    p.residual = e->y; p.out_stats = e->stats_x; p.f16_operands = 1;   // h and W2 are fp16
+    // res_raw = h . W2^T + b_2 + LN_1(mid_raw)   (+ row statistics of res_raw); LN_2 is applied by the consumers
+    p.N = HIDDEN; p.K = sh.inter; p.colc = nullptr; p.cold = L.down_cold; p.gamma = L.down_gamma; p.in_stats = mid_stats;
+    p.residual = mid; p.out_stats = res_stats; p.f16_operands = 1;   // h and W2 are fp16
     {
-      ProfScope prof(e, KC_GEMM_DOWN_LN, st);
-      rc = (e->gemm_pairs & 8) ? DRAG_GEMM2_RES(e, e->tm_h, L.tp_down, e->ts_x, e->ts_y, p, st) : DRAG_GEMM_RES(e, e->tm_h, L.tm_down, e->ts_x, e->ts_y, p, st);
+      ProfScope prof(e, ws, last_cls ? KC_CLS_TAIL : KC_GEMM_DOWN_LN, st);
+      rc = (e->gemm_pairs & 8) ? DRAG_GEMM2_RES(e, ws.tm_h, L.tp_down, *ts_res, *ts_mid, p, st) : DRAG_GEMM_RES(e, ws.tm_h, L.tm_down, *ts_res, *ts_mid, p, st);
     }
     if (rc) return rc;
+    (void)tm_res;
   }
   // LayerNorm that turns the current raw hidden state into the model's hidden state
   const float* fin_g = n_layers == 0 ? e->emb_g : e->layers[n_layers - 1].ln2_g;
   const float* fin_b = n_layers == 0 ? e->emb_b : e->layers[n_layers - 1].ln2_b;
   if (tap) {
-    ln_apply_kernel<<<(total + 7) / 8, 256, 0, st>>>(e->x, e->stats_x, fin_g, fin_b, sh.ln_eps, total, d_hidden);
+    ln_apply_kernel<<<(total + 7) / 8, 256, 0, st>>>(ws.x, ws.stats_x, fin_g, fin_b, sh.ln_eps, total, d_hidden);
     DRAG_CUDA_OK(cudaGetLastError());
   }
   if (d_out) {
-    ProfScope prof(e, KC_POOL, st);
+    ProfScope prof(e, ws, KC_POOL, st);
     const int blocks = (n_seq + 7) / 8;
-    pool_normalize_kernel<<<blocks, 256, 0, st>>>(e->x, e->stats_x, fin_g, fin_b, sh.ln_eps, d_cu, n_seq, d_out);
+    if (cls_tail)   // the last layer left compact rows (row = sequence) in y
+      pool_normalize_kernel<<<blocks, 256, 0, st>>>(ws.y, ws.stats_y, fin_g, fin_b, sh.ln_eps, nullptr, n_seq, d_out);
+    else
+      pool_normalize_kernel<<<blocks, 256, 0, st>>>(ws.x, ws.stats_x, fin_g, fin_b, sh.ln_eps, d_cu, n_seq, d_out);
     DRAG_CUDA_OK(cudaGetLastError());
   }
   return DRAG_OK;
@@ -527,6 +663,74 @@ int upload_sum_f32(drag_encoder* e, float** dst, const float* a, const float* b,
   std::vector<float> tmp(n);
   for (size_t i = 0; i < n; ++i) tmp[i] = a[i] + b[i];
   return upload_f32(e, dst, tmp.data(), n);
+}
+
+int init_workspace(drag_encoder* e, Workspace& ws, int64_t tokens, bool high_priority) {
+  int rc;
+  const size_t H = HIDDEN, F = e->shape.inter;
+  ws.max_tokens = (tokens + 127) / 128 * 128;
+  const size_t T = (size_t)ws.max_tokens;
+  if ((rc = dev_alloc(e, &ws.x, T * H))) return rc;
+  if ((rc = dev_alloc(e, &ws.y, T * H))) return rc;
+  if ((rc = dev_alloc(e, &ws.ctx, T * H))) return rc;
+  if ((rc = dev_alloc(e, &ws.qkv, T * 3 * H))) return rc;
+  if ((rc = dev_alloc(e, &ws.h, T * F))) return rc;
+  if ((rc = dev_alloc(e, &ws.stats_x, T * PARTS))) return rc;
+  if ((rc = dev_alloc(e, &ws.stats_y, T * PARTS))) return rc;
+  // activations are zeroed once so that the tail rows of the last 128-row tile hold finite values
+  DRAG_CUDA_OK(cudaMemset(ws.x, 0, T * H * 2));
+  DRAG_CUDA_OK(cudaMemset(ws.y, 0, T * H * 2));
+  DRAG_CUDA_OK(cudaMemset(ws.ctx, 0, T * H * 2));
+  DRAG_CUDA_OK(cudaMemset(ws.qkv, 0, T * 3 * H * 2));
+  DRAG_CUDA_OK(cudaMemset(ws.h, 0, T * F * 2));
+  DRAG_CUDA_OK(cudaMemset(ws.stats_x, 0, T * PARTS * 8));
+  DRAG_CUDA_OK(cudaMemset(ws.stats_y, 0, T * PARTS * 8));
+  if ((rc = make_tmap(&ws.tm_x, ws.x, T, H, gemm::BLOCK_M))) return rc;
+  if ((rc = make_tmap(&ws.tm_y, ws.y, T, H, gemm::BLOCK_M))) return rc;
+  if ((rc = make_tmap(&ws.tm_ctx, ws.ctx, T, H, gemm::BLOCK_M))) return rc;
+  if ((rc = make_tmap(&ws.tm_h, ws.h, T, F, gemm::BLOCK_M))) return rc;
+  if ((rc = make_tmap(&ws.ts_x, ws.x, T, H, gemm::STORE_ROWS))) return rc;
+  if ((rc = make_tmap(&ws.ts_y, ws.y, T, H, gemm::STORE_ROWS))) return rc;
+  if ((rc = make_tmap(&ws.ts_qkv, ws.qkv, T, 3 * H, gemm::STORE_ROWS))) return rc;
+  if ((rc = make_tmap(&ws.ts_h, ws.h, T, F, gemm::STORE_ROWS))) return rc;
+  if ((rc = make_tmap_bf16_box(&ws.tm_qkv_heads, ws.qkv, T, 3 * H, attn3::TILE, attn3::HEAD_DIM))) return rc;
+  // host-buffer path: own stream, pinned staging + device mirrors
+  int lo = 0, hi = 0;
+  DRAG_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = greatest priority (numerically lowest)
+  DRAG_CUDA_OK(cudaStreamCreateWithPriority(&ws.stream, cudaStreamNonBlocking, high_priority ? hi : lo));
+  DRAG_CUDA_OK(cudaEventCreateWithFlags(&ws.done, cudaEventDisableTiming));
+  if ((rc = dev_alloc(e, &ws.d_ids, T))) return rc;
+  if ((rc = dev_alloc(e, &ws.d_cu, T + 1))) return rc;
+  if (cudaMallocHost((void**)&ws.p_ids, T * 4) != cudaSuccess || cudaMallocHost((void**)&ws.p_cu, (T + 1) * 4) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(DRAG_ERR_NOMEM, "cudaMallocHost failed");
+  }
+  return DRAG_OK;
+}
+
+void free_workspace(Workspace& ws) {
+  if (ws.stream) { cudaStreamSynchronize(ws.stream); cudaStreamDestroy(ws.stream); }
+  if (ws.done) cudaEventDestroy(ws.done);
+  if (ws.p_ids) cudaFreeHost(ws.p_ids);
+  if (ws.p_cu) cudaFreeHost(ws.p_cu);
+  if (ws.p_out) cudaFreeHost(ws.p_out);
+  if (ws.d_out) cudaFree(ws.d_out);
+}
+
+// the workspace a forward over `total` tokens runs in: small batches (the query path) get the query workspace
+Workspace& pick_workspace(drag_encoder* e, int64_t total) {
+  return total <= e->ws[1].max_tokens ? e->ws[1] : e->ws[0];
+}
+
+// One forward enqueued on `st` inside workspace `ws` (caller holds ws.lock): the previous forward that used the
+// workspace -- on whatever stream -- is waited for in-stream first, and this one leaves its own marker behind.
+int forward_locked(drag_encoder* e, Workspace& ws, const int32_t* d_ids, const int32_t* d_cu, const int32_t* h_cu, int n_seq,
+                   float* d_out, int stop_after_layer, float* d_hidden, cudaStream_t st) {
+  if (ws.used) DRAG_CUDA_OK(cudaStreamWaitEvent(st, ws.done, 0));
+  const int rc = forward_impl(e, ws, d_ids, d_cu, h_cu, n_seq, d_out, stop_after_layer, d_hidden, st);
+  ws.used = true;
+  DRAG_CUDA_OK(cudaEventRecord(ws.done, st));   // also after a failed enqueue: kernels launched so far still use the buffers
+  return rc;
 }
 
 }  // namespace
@@ -592,41 +796,20 @@ extern "C" int drag_encoder_create(const drag_bert_shape* shape, const float* co
     if ((rc = make_tmap(&L.tp_up, L.w_up, F, H, FFN_BLOCK_N_PAIR / 2))) return bail(rc);
     if ((rc = make_tmap(&L.tp_down, L.w_down, H, F, RES_BLOCK_N_PAIR / 2))) return bail(rc);
   }
-  const size_t T = (size_t)e->max_tokens;
-  if ((rc = dev_alloc(e, &e->x, T * H))) return bail(rc);
-  if ((rc = dev_alloc(e, &e->y, T * H))) return bail(rc);
-  if ((rc = dev_alloc(e, &e->ctx, T * H))) return bail(rc);
-  if ((rc = dev_alloc(e, &e->qkv, T * 3 * H))) return bail(rc);
-  if ((rc = dev_alloc(e, &e->h, T * F))) return bail(rc);
-  if ((rc = dev_alloc(e, &e->stats_x, T * PARTS))) return bail(rc);
-  if ((rc = dev_alloc(e, &e->stats_y, T * PARTS))) return bail(rc);
-  // activations are zeroed once so that the tail rows of the last 128-row tile hold finite values
-  cudaMemset(e->x, 0, T * H * 2); cudaMemset(e->y, 0, T * H * 2); cudaMemset(e->ctx, 0, T * H * 2);
-  cudaMemset(e->qkv, 0, T * 3 * H * 2); cudaMemset(e->h, 0, T * F * 2);
-  cudaMemset(e->stats_x, 0, T * PARTS * 8); cudaMemset(e->stats_y, 0, T * PARTS * 8);
-  if ((rc = make_tmap(&e->tm_x, e->x, T, H, gemm::BLOCK_M))) return bail(rc);
-  if ((rc = make_tmap(&e->tm_y, e->y, T, H, gemm::BLOCK_M))) return bail(rc);
-  if ((rc = make_tmap(&e->tm_ctx, e->ctx, T, H, gemm::BLOCK_M))) return bail(rc);
-  if ((rc = make_tmap(&e->tm_h, e->h, T, F, gemm::BLOCK_M))) return bail(rc);
-  if ((rc = make_tmap(&e->ts_x, e->x, T, H, gemm::STORE_ROWS))) return bail(rc);
-  if ((rc = make_tmap(&e->ts_y, e->y, T, H, gemm::STORE_ROWS))) return bail(rc);
-  if ((rc = make_tmap(&e->ts_qkv, e->qkv, T, 3 * H, gemm::STORE_ROWS))) return bail(rc);
-  if ((rc = make_tmap(&e->ts_h, e->h, T, F, gemm::STORE_ROWS))) return bail(rc);
-  if ((rc = make_tmap_bf16_box(&e->tm_qkv_heads, e->qkv, T, 3 * H, attn_tc::TILE, attn_tc::HEAD_DIM))) return bail(rc);
+  if ((rc = init_workspace(e, e->ws[0], e->max_tokens, false))) return bail(rc);
+  if ((rc = init_workspace(e, e->ws[1], e->max_tokens < QUERY_WORKSPACE_TOKENS ? e->max_tokens : QUERY_WORKSPACE_TOKENS, true))) return bail(rc);
   {
     const char* v = getenv("DRAG_ATTENTION");
     if (v && strcmp(v, "tc") == 0) e->attention_variant = 1;
     if (v && strcmp(v, "tc2") == 0) e->attention_variant = 2;
+    if (v && strcmp(v, "tc3") == 0) e->attention_variant = 3;
+    if (v && strcmp(v, "tc3p2") == 0) e->attention_variant = 4;
     const char* gm = getenv("DRAG_GEMM_PAIRS");
     if (gm && gm[0] >= '0' && gm[0] <= '9') e->gemm_pairs = atoi(gm) & 31;
+    const char* co = getenv("DRAG_CLS_ONLY");
+    if (co && co[0] == '0') e->cls_only = false;
   }
 
-  // host-buffer path: pinned staging + device mirrors
-  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(DRAG_ERR_CUDA, "cudaStreamCreate failed"));
-  if ((rc = dev_alloc(e, &e->d_ids, T))) return bail(rc);
-  if ((rc = dev_alloc(e, &e->d_cu, T + 1))) return bail(rc);
-  if (cudaMallocHost((void**)&e->p_ids, T * 4) != cudaSuccess || cudaMallocHost((void**)&e->p_cu, (T + 1) * 4) != cudaSuccess)
-    return bail(fail(DRAG_ERR_NOMEM, "cudaMallocHost failed"));
   // the attention kernels need > 48 KB of dynamic shared memory
   if ((rc = attention_set_attributes())) return bail(rc);
   if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(DRAG_ERR_CUDA, "weight upload failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -637,26 +820,26 @@ extern "C" int drag_encoder_create(const drag_bert_shape* shape, const float* co
 extern "C" int drag_encoder_destroy(drag_encoder* e) {
   if (!e) return DRAG_OK;
   DeviceGuard guard(e->device);
-  if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
+  free_workspace(e->ws[0]);
+  free_workspace(e->ws[1]);
   for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
   for (void* p : e->allocs) cudaFree(p);
-  if (e->p_ids) cudaFreeHost(e->p_ids);
-  if (e->p_cu) cudaFreeHost(e->p_cu);
-  if (e->p_out) cudaFreeHost(e->p_out);
-  if (e->d_out) cudaFree(e->d_out);
   cudaGetLastError();
   delete e;
   return DRAG_OK;
 }
 
+static int64_t total_tokens_of(const int32_t* h_cu, int n_seq) { return (h_cu && n_seq > 0) ? (int64_t)h_cu[n_seq] : 0; }
+
 extern "C" int drag_encoder_forward(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu_seqlens,
                                     const int32_t* h_cu_seqlens, int n_seq, float* d_out, void* stream) {
   DRAG_REQUIRE(e, "drag_encoder_forward: null encoder");
   DRAG_REQUIRE(d_out || n_seq == 0, "drag_encoder_forward: null output");
-  std::lock_guard<std::mutex> hold(e->lock);
+  Workspace& ws = pick_workspace(e, total_tokens_of(h_cu_seqlens, n_seq));
+  std::lock_guard<std::mutex> hold(ws.lock);
   DeviceGuard guard(e->device);
   if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_encoder_forward: cannot select device %d", e->device);
-  return forward_impl(e, d_ids, d_cu_seqlens, h_cu_seqlens, n_seq, d_out, -1, nullptr, (cudaStream_t)stream);
+  return forward_locked(e, ws, d_ids, d_cu_seqlens, h_cu_seqlens, n_seq, d_out, -1, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int drag_encoder_forward_debug(drag_encoder* e, const int32_t* d_ids, const int32_t* d_cu_seqlens,
@@ -664,10 +847,11 @@ extern "C" int drag_encoder_forward_debug(drag_encoder* e, const int32_t* d_ids,
                                           void* stream) {
   DRAG_REQUIRE(e && d_hidden, "drag_encoder_forward_debug: null pointer");
   DRAG_REQUIRE(stop_after_layer >= 0 && stop_after_layer <= e->shape.layers, "drag_encoder_forward_debug: bad layer %d", stop_after_layer);
-  std::lock_guard<std::mutex> hold(e->lock);
+  Workspace& ws = pick_workspace(e, total_tokens_of(h_cu_seqlens, n_seq));
+  std::lock_guard<std::mutex> hold(ws.lock);
   DeviceGuard guard(e->device);
   if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_encoder_forward_debug: cannot select device %d", e->device);
-  return forward_impl(e, d_ids, d_cu_seqlens, h_cu_seqlens, n_seq, nullptr, stop_after_layer, d_hidden, (cudaStream_t)stream);
+  return forward_locked(e, ws, d_ids, d_cu_seqlens, h_cu_seqlens, n_seq, nullptr, stop_after_layer, d_hidden, (cudaStream_t)stream);
 }
 
 extern "C" int drag_encoder_embed_host(drag_encoder* e, const int32_t* h_ids, const int32_t* h_cu_seqlens, int n_seq,
@@ -675,34 +859,36 @@ extern "C" int drag_encoder_embed_host(drag_encoder* e, const int32_t* h_ids, co
   DRAG_REQUIRE(e, "drag_encoder_embed_host: null encoder");
   if (n_seq == 0) return DRAG_OK;
   DRAG_REQUIRE(h_ids && h_cu_seqlens && h_out && n_seq > 0, "drag_encoder_embed_host: null pointer");
-  std::lock_guard<std::mutex> hold(e->lock);
-  DeviceGuard guard(e->device);
-  if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_encoder_embed_host: cannot select device %d", e->device);
   const int64_t total = h_cu_seqlens[n_seq];
   DRAG_REQUIRE(total >= n_seq && total <= e->max_tokens, "drag_encoder_embed_host: %lld tokens exceed max_tokens=%lld", (long long)total, (long long)e->max_tokens);
+  Workspace& ws = pick_workspace(e, total);
+  std::lock_guard<std::mutex> hold(ws.lock);
+  DeviceGuard guard(e->device);
+  if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_encoder_embed_host: cannot select device %d", e->device);
   // output staging grows on demand (power-of-two capacity)
-  if (n_seq > e->out_cap) {
+  if (n_seq > ws.out_cap) {
     int64_t want = 1024;
     while (want < n_seq) want <<= 1;
-    if (e->d_out) cudaFree(e->d_out);
-    if (e->p_out) cudaFreeHost(e->p_out);
-    e->d_out = nullptr; e->p_out = nullptr; e->out_cap = 0;
-    if (cudaMalloc((void**)&e->d_out, (size_t)want * HIDDEN * 4) != cudaSuccess ||
-        cudaMallocHost((void**)&e->p_out, (size_t)want * HIDDEN * 4) != cudaSuccess) {
+    DRAG_CUDA_OK(cudaStreamSynchronize(ws.stream));
+    if (ws.d_out) cudaFree(ws.d_out);
+    if (ws.p_out) cudaFreeHost(ws.p_out);
+    ws.d_out = nullptr; ws.p_out = nullptr; ws.out_cap = 0;
+    if (cudaMalloc((void**)&ws.d_out, (size_t)want * HIDDEN * 4) != cudaSuccess ||
+        cudaMallocHost((void**)&ws.p_out, (size_t)want * HIDDEN * 4) != cudaSuccess) {
       cudaGetLastError();
       return fail(DRAG_ERR_NOMEM, "drag_encoder_embed_host: cannot allocate output staging for %lld sequences", (long long)want);
     }
-    e->out_cap = want;
+    ws.out_cap = want;
   }
-  memcpy(e->p_ids, h_ids, (size_t)total * 4);
-  memcpy(e->p_cu, h_cu_seqlens, (size_t)(n_seq + 1) * 4);
-  DRAG_CUDA_OK(cudaMemcpyAsync(e->d_ids, e->p_ids, (size_t)total * 4, cudaMemcpyHostToDevice, e->stream));
-  DRAG_CUDA_OK(cudaMemcpyAsync(e->d_cu, e->p_cu, (size_t)(n_seq + 1) * 4, cudaMemcpyHostToDevice, e->stream));
-  int rc = forward_impl(e, e->d_ids, e->d_cu, e->p_cu, n_seq, e->d_out, -1, nullptr, e->stream);
-  if (rc) return rc;
-  DRAG_CUDA_OK(cudaMemcpyAsync(e->p_out, e->d_out, (size_t)n_seq * HIDDEN * 4, cudaMemcpyDeviceToHost, e->stream));
-  DRAG_CUDA_OK(cudaStreamSynchronize(e->stream));
-  memcpy(h_out, e->p_out, (size_t)n_seq * HIDDEN * 4);
+  memcpy(ws.p_ids, h_ids, (size_t)total * 4);
+  memcpy(ws.p_cu, h_cu_seqlens, (size_t)(n_seq + 1) * 4);
+  DRAG_CUDA_OK(cudaMemcpyAsync(ws.d_ids, ws.p_ids, (size_t)total * 4, cudaMemcpyHostToDevice, ws.stream));
+  DRAG_CUDA_OK(cudaMemcpyAsync(ws.d_cu, ws.p_cu, (size_t)(n_seq + 1) * 4, cudaMemcpyHostToDevice, ws.stream));
+  int rc = forward_locked(e, ws, ws.d_ids, ws.d_cu, ws.p_cu, n_seq, ws.d_out, -1, nullptr, ws.stream);
+  if (rc) { cudaStreamSynchronize(ws.stream); return rc; }
+  DRAG_CUDA_OK(cudaMemcpyAsync(ws.p_out, ws.d_out, (size_t)n_seq * HIDDEN * 4, cudaMemcpyDeviceToHost, ws.stream));
+  DRAG_CUDA_OK(cudaStreamSynchronize(ws.stream));
+  memcpy(h_out, ws.p_out, (size_t)n_seq * HIDDEN * 4);
   return DRAG_OK;
 }
 
@@ -766,7 +952,7 @@ extern "C" int drag_debug_attention(int device, int variant, const void* d_qkv, 
                                     int n_seq, int n_tokens, int max_len, int heads, void* stream) {
   DRAG_REQUIRE(d_qkv && d_ctx && d_cu_seqlens && n_seq >= 1 && heads >= 1 && n_tokens >= 1, "drag_debug_attention: bad arguments");
   DRAG_REQUIRE(max_len >= 1 && max_len <= 512, "drag_debug_attention: max_len must be in 1..512");
-  DRAG_REQUIRE(variant >= 0 && variant <= 2, "drag_debug_attention: variant 0 (mma.sync), 1 (tcgen05) or 2 (tcgen05, exact single-pass softmax)");
+  DRAG_REQUIRE(variant >= 0 && variant <= 4, "drag_debug_attention: variant 0 (mma.sync), 1, 2 (earlier tcgen05 designs), 3 / 4 (tcgen05, two softmax groups; 4 double-buffers P)");
   DeviceGuard guard(device);
   if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_debug_attention: cannot select device %d", device);
   int rc = attention_set_attributes();
@@ -783,7 +969,7 @@ extern "C" int drag_debug_attention(int device, int variant, const void* d_qkv, 
 // ---------------------------------------------------------------------------------
 extern "C" int drag_encoder_profile_begin(drag_encoder* e, int max_launches) {
   DRAG_REQUIRE(e && max_launches >= 1 && max_launches <= (1 << 20), "drag_encoder_profile_begin: bad arguments");
-  std::lock_guard<std::mutex> hold(e->lock);
+  std::lock_guard<std::mutex> hold(e->ws[0].lock);
   DeviceGuard guard(e->device);
   while (e->prof_events.size() < (size_t)max_launches * 2) {
     cudaEvent_t ev;
@@ -796,11 +982,11 @@ extern "C" int drag_encoder_profile_begin(drag_encoder* e, int max_launches) {
   return DRAG_OK;
 }
 
-// ms_by_class / launches_by_class: arrays of 7 (embed, gemm_qkv, attention, gemm_out_ln, gemm_up_gelu,
-// gemm_down_ln, pool).  The caller must have synchronised the stream(s) the forwards ran on.
+// ms_by_class / launches_by_class: arrays of 8 (embed, gemm_qkv, attention, gemm_out_ln, gemm_up_gelu,
+// gemm_down_ln, pool, cls_tail = the CLS-only kernels of the last layer).  The caller must have synchronised the stream(s) the forwards ran on.
 extern "C" int drag_encoder_profile_end(drag_encoder* e, double* ms_by_class, int* launches_by_class) {
   DRAG_REQUIRE(e && ms_by_class && launches_by_class, "drag_encoder_profile_end: null pointer");
-  std::lock_guard<std::mutex> hold(e->lock);
+  std::lock_guard<std::mutex> hold(e->ws[0].lock);
   DeviceGuard guard(e->device);
   e->profiling = false;
   for (int i = 0; i < KC_COUNT; ++i) { ms_by_class[i] = 0.0; launches_by_class[i] = 0; }

@@ -99,6 +99,19 @@ class DeviceMatrix:
         self._batch_state = None
         self.last_batch_fallbacks = 0
 
+    def nbytes(self) -> int:
+        """Device bytes this index pins right now (rows, squared norms, id maps and -- once a query batch has built
+        it -- the bf16 scoring copy and inverse norms of the batched path)."""
+        total = self.matrix.numel() * self.matrix.element_size() + self.row_sq.numel() * 4 + self.doc_offsets.numel() * 8
+        if self.chunk_ids is not None:
+            total += self.chunk_ids.numel() * 8
+        state = self._batch_state
+        if state and state.get("ok") is not None and "shadow" in state:
+            if state["shadow"] is not self.matrix:
+                total += state["shadow"].numel() * 2
+            total += state["inv"].numel() * 4
+        return int(total)
+
     # ------------------------------------------------------------------ helpers
     def _check_queries(self, queries: np.ndarray) -> np.ndarray:
         q = np.asarray(queries)

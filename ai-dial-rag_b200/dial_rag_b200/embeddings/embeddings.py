@@ -105,6 +105,12 @@ class B200BgeEmbeddings(Embeddings):
         prepared = self.query_instruction + text.replace("\n", " ")
         return self.client.embed_packed(*self.tokenizer.encode_packed([prepared], n_threads=1))[0].tolist()
 
+    def embed_queries_numpy(self, texts: Sequence[str]) -> np.ndarray:
+        """Many queries in ONE packed forward (the batched retriever entry points): float32 ``[n, 384]``, row i
+        bit-identical to ``embed_query(texts[i])`` (an embedding does not depend on the batch composition)."""
+        prepared = [self.query_instruction + t.replace("\n", " ") for t in texts]
+        return self.embed_packed_numpy(*self.tokenizer.encode_packed(prepared, n_threads=1 if len(prepared) < 16 else 0))
+
 
 _impl: Optional[B200BgeEmbeddings] = None
 _impl_lock = threading.Lock()
@@ -155,6 +161,12 @@ class AsyncEmbeddings(Embeddings):
 
     async def aembed_query(self, text: str) -> List[float]:
         return await run_in_query_embeddings_pool(bge_embedding_impl().embed_query, text)
+
+    def embed_queries_numpy(self, texts: List[str]) -> np.ndarray:
+        return bge_embedding_impl().embed_queries_numpy(texts)
+
+    async def aembed_queries_numpy(self, texts: List[str]) -> np.ndarray:
+        return await run_in_query_embeddings_pool(bge_embedding_impl().embed_queries_numpy, texts)
 
 
 bge_embedding = AsyncEmbeddings()

@@ -192,13 +192,14 @@ class B200Encoder:
         return hidden.cpu().numpy()
 
     # ------------------------------------------------------------------ profiling (bench.py)
-    KERNEL_CLASSES = ("embed_ln", "gemm_qkv", "attention", "gemm_out_ln", "gemm_up_gelu", "gemm_down_ln", "pool_normalize")
+    KERNEL_CLASSES = ("embed_ln", "gemm_qkv", "attention", "gemm_out_ln", "gemm_up_gelu", "gemm_down_ln", "pool_normalize",
+                      "cls_tail")
 
     def profile_begin(self, max_launches: int = 8192) -> None:
         _native.check(self.lib.drag_encoder_profile_begin(self._handle, int(max_launches)))
 
     def profile_end(self) -> Dict[str, Dict[str, float]]:
-        ms = (C.c_double * 7)()
-        n = (C.c_int * 7)()
+        ms = (C.c_double * len(self.KERNEL_CLASSES))()
+        n = (C.c_int * len(self.KERNEL_CLASSES))()
         _native.check(self.lib.drag_encoder_profile_end(self._handle, ms, n))
         return {k: {"ms": ms[i], "launches": n[i]} for i, k in enumerate(self.KERNEL_CLASSES)}

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import os
 import threading
+import uuid
 import weakref
 from collections import OrderedDict
 from typing import Iterable, List, Optional, Sequence, Tuple
@@ -82,65 +83,95 @@ def _stack_documents(doc_indexes: Sequence[DocIndex]):
 
 
 
+UID_PREFIX = "drag-"   # ItemEmbeddings.id of the first item of an index built by this package: "drag-<uuid4 hex>"
+
+
+def _tag(a: np.ndarray) -> int:
+    return hash(np.ascontiguousarray(a).tobytes())
+
+
+def source_key(src) -> tuple:
+    """A key of one document's persisted ``MultiEmbeddings`` that is STABLE ACROSS DESERIALISATION.
+
+    The reference's record cache holds the *serialised bytes* (index_storage.py:56-66, ``LRUCacheStorage``) and
+    ``DocumentRecord.from_bytes`` runs on every load (index_storage.py:136), so every request sees fresh Python
+    objects: object identity cannot key anything.  What does survive pickle + gzip is the content:
+      * indexes built by this package carry a build id in a field the reference persists but never reads
+        (``ItemEmbeddings.id`` of the first item, document_record.py:32-36): the key is that id plus the item
+        count, the width and a fingerprint of the first and last item -- O(1) per request;
+      * anything else (indexes written by the stock reference) is keyed by a blake2b digest of all rows.
+    """
+    n = len(src)
+    if n == 0:
+        return ("empty",)
+    first = np.asarray(src[0].embeddings)
+    uid = getattr(src[0], "id", None)
+    if isinstance(uid, str) and uid.startswith(UID_PREFIX):
+        last = np.asarray(src[-1].embeddings)
+        return ("uid", uid, n, first.shape, last.shape, str(first.dtype), _tag(first), _tag(last))
+    import hashlib
+
+    h = hashlib.blake2b(digest_size=16)
+    rows = 0
+    for item in src:
+        a = np.ascontiguousarray(item.embeddings)
+        rows += len(a)
+        h.update(a.data if a.size else b"")
+        h.update(b"|")
+    return ("content", h.digest(), n, rows, str(first.dtype))
+
+
 class ResidentIndexCache:
     """Device-resident indexes kept ACROSS requests.
 
     The reference rebuilds its flat host arrays on every request (retrieval_chain.py:264-271 ->
-    ``from_doc_records``); with the matrix in HBM that would mean re-flattening and re-uploading it
-    per request.  The persisted per-document ``MultiEmbeddings`` objects, however, are the same Python
-    objects from request to request (the reference caches loaded ``DocumentRecord``s), so an index is
-    keyed by the IDENTITY of its source objects.  An entry holds only weak references to them: when a
-    source is collected or its length changes the entry is dropped, so a recycled ``id()`` can never
-    alias.  Least-recently-used entries are evicted beyond ``max_bytes`` (``DRAG_INDEX_CACHE_MB``,
-    default 16384) or ``max_entries``.
+    ``from_doc_records``); with the matrix in HBM that would mean re-flattening and re-uploading it per request.
+    Entries are keyed by VALUE (``source_key``: build id or content digest of every document, in order), so a
+    request whose records were freshly deserialised from the same stored bytes hits.  Least-recently-used entries
+    are evicted beyond ``max_bytes`` (``DRAG_INDEX_CACHE_MB``, default 16384; the bytes an entry pins are asked of
+    the entry at eviction time, so a scoring copy made after insertion counts) or ``max_entries``.  No weak
+    references, no callbacks: nothing can re-enter the lock.
     """
 
     def __init__(self, max_entries: int = 16, max_bytes: Optional[int] = None):
         if max_bytes is None:
             max_bytes = int(os.environ.get("DRAG_INDEX_CACHE_MB", "16384")) << 20
         self.max_entries, self.max_bytes = int(max_entries), int(max_bytes)
-        self._entries: "OrderedDict[tuple, tuple]" = OrderedDict()   # key -> (weakrefs, lengths, value, nbytes)
-        self._lock = threading.Lock()
+        self._entries: "OrderedDict[tuple, tuple]" = OrderedDict()   # key -> (value, nbytes callable)
+        self._lock = threading.RLock()
         self.hits = self.misses = 0
 
     @staticmethod
     def _key(sources: Sequence[object], extra: tuple) -> tuple:
-        return tuple(id(s) for s in sources) + ("|",) + tuple(extra)
+        return tuple(source_key(s) for s in sources) + ("|",) + tuple(extra)
 
-    def get(self, sources: Sequence[object], extra: tuple = ()):
-        key = self._key(sources, extra)
+    def get(self, sources: Sequence[object], extra: tuple = (), key: Optional[tuple] = None):
+        key = self._key(sources, extra) if key is None else key
         with self._lock:
             entry = self._entries.get(key)
             if entry is not None:
-                refs, lengths, value, _ = entry
-                alive = all(r() is s for r, s in zip(refs, sources, strict=True))
-                if alive and lengths == tuple(len(s) for s in sources):
-                    self._entries.move_to_end(key)
-                    self.hits += 1
-                    return value
-                del self._entries[key]
+                self._entries.move_to_end(key)
+                self.hits += 1
+                return entry[0]
             self.misses += 1
             return None
 
-    def put(self, sources: Sequence[object], extra: tuple, value, nbytes: int) -> bool:
-        key = self._key(sources, extra)
-        try:
-            # a collected source drops the entry right away (frees the HBM it pins)
-            refs = tuple(weakref.ref(s, lambda _r, k=key: self._drop(k)) for s in sources)
-        except TypeError:
-            return False   # sources that cannot be weakly referenced are not cached
+    def put(self, sources: Sequence[object], extra: tuple, value, nbytes, key: Optional[tuple] = None) -> bool:
+        """``nbytes``: an int, or a callable returning the bytes the entry pins right now."""
+        key = self._key(sources, extra) if key is None else key
+        size = nbytes if callable(nbytes) else (lambda n=int(nbytes): n)
         with self._lock:
-            self._entries[key] = (refs, tuple(len(s) for s in sources), value, int(nbytes))
+            self._entries[key] = (value, size)
             self._entries.move_to_end(key)
             while len(self._entries) > self.max_entries or (
-                len(self._entries) > 1 and sum(e[3] for e in self._entries.values()) > self.max_bytes
+                len(self._entries) > 1 and sum(e[1]() for e in self._entries.values()) > self.max_bytes
             ):
                 self._entries.popitem(last=False)
         return True
 
-    def _drop(self, key: tuple) -> None:
+    def nbytes(self) -> int:
         with self._lock:
-            self._entries.pop(key, None)
+            return sum(e[1]() for e in self._entries.values())
 
     def clear(self) -> None:
         with self._lock:
@@ -199,18 +230,20 @@ class EmbeddingsIndex:
         cache: Optional["ResidentIndexCache"] = None,
     ) -> "EmbeddingsIndex":
         """An index over per-document ``MultiEmbeddings`` (one row per chunk, ``create_index_by_chunk``) whose
-        device-resident matrix is shared between requests through ``cache`` (default: the process-wide one)."""
+        device-resident matrix is shared between requests through ``cache`` (default: the process-wide one),
+        keyed by the documents' build ids / content (``source_key``): records deserialised afresh from the same
+        stored bytes reuse the matrix already in HBM."""
         cache = RESIDENT_INDEXES if cache is None else cache
         sources = list(sources)
         index = cls(retrieval_type, None, metric=metric, limit=limit, device=device, storage=storage)  # type: ignore[arg-type]
         index._sources = sources
-        hit = cache.get(sources, (storage, device))
+        key = cache._key(sources, (storage, device))
+        hit = cache.get(sources, key=key)
         if hit is not None:
             index._resident, index._resident_empty = hit
             return index
         matrix = index._matrix()   # flattens (doc_indexes) and uploads
-        nbytes = 0 if matrix is None else matrix.n_rows * matrix.dim * (4 if storage == "f32" else 2)
-        cache.put(sources, (storage, device), (matrix, matrix is None), nbytes)
+        cache.put(sources, (storage, device), (matrix, matrix is None), (lambda: 0) if matrix is None else matrix.nbytes, key=key)
         return index
 
     # The matrix is uploaded on first use and then stays in HBM for the life of the
@@ -282,34 +315,72 @@ def _rows_of(item) -> np.ndarray:
     return np.asarray(item.embeddings)
 
 
+def _new_uid() -> str:
+    return UID_PREFIX + uuid.uuid4().hex
+
+
+# Containers built by ``pack_embedding_matrix`` keep their rows in ONE contiguous matrix (every item is a [1, dim]
+# view of it).  The matrix is remembered per container (weakly, by identity: this is an in-process shortcut for the
+# build -> search flow of one request, not a cache key) so that flattening is O(1) instead of a loop over n items.
+_CONTIGUOUS: dict = {}
+
+
+def _remember_contiguous(multi, matrix: np.ndarray) -> None:
+    key = id(multi)
+    try:
+        _CONTIGUOUS[key] = (weakref.ref(multi, lambda _r, k=key: _CONTIGUOUS.pop(k, None)), matrix)
+    except TypeError:   # container type without weak-reference support
+        pass
+
+
+def _contiguous_matrix(multi) -> Optional[np.ndarray]:
+    """The [n, dim] matrix behind ``multi`` if it still is n ordered [1, dim] views of it (length and the first,
+    middle and last item are verified: same memory, same shape)."""
+    entry = _CONTIGUOUS.get(id(multi))
+    if entry is None or entry[0]() is not multi:
+        return None
+    matrix = entry[1]
+    n = len(multi)
+    if n != len(matrix) or n == 0:
+        return None
+    for i in {0, n // 2, n - 1}:
+        rows = _rows_of(multi[i])
+        if rows.shape != (1, matrix.shape[1]) or rows.dtype != matrix.dtype or \
+                rows.__array_interface__["data"][0] != matrix[i : i + 1].__array_interface__["data"][0]:
+            return None
+    return matrix
+
+
+def _flatten(items: Sequence, owner_of_item, dtype) -> DocIndex:
+    """Rows of ``items`` back to back + the owner id of every row; ``dtype=None`` keeps the items' dtype
+    (``np.array(list_of_rows)``, embeddings_index.py:133-136), else casts (``:115-118``)."""
+    lens = np.fromiter((len(_rows_of(it)) for it in items), dtype=np.int64, count=len(items))
+    owners = np.repeat(np.asarray(owner_of_item, dtype=np.int64), lens)
+    blocks = [_rows_of(it) for it, n in zip(items, lens) if n]
+    if not blocks:
+        # the reference builds np.array([]) here: float64 without a dtype, float32 with one
+        return DocIndex(chunk_ids=owners, embeddings=np.array([], dtype=dtype))
+    blocks = [b.reshape(len(b), -1) for b in blocks]
+    flat = np.concatenate(blocks)
+    return DocIndex(chunk_ids=owners, embeddings=flat if dtype is None else flat.astype(dtype, copy=False))
+
+
 def create_index_by_page(chunks: Sequence[Chunk], pages_embeddings: MultiEmbeddings | None) -> DocIndex:
-    """Every chunk gets all rows of its page (embeddings_index.py:101-118)."""
+    """Every chunk gets all rows of its page, in chunk order (embeddings_index.py:101-118)."""
     if pages_embeddings is None:
         return DocIndex()
-    owners, blocks = [], []
-    for i, chunk in enumerate(chunks):
-        rows = _rows_of(pages_embeddings[_get_page_index(chunk)])
-        owners.append(np.full(len(rows), i, dtype=np.int64))
-        if len(rows):
-            blocks.append(rows.reshape(len(rows), -1))
-    if not blocks:
-        return DocIndex(np.array([], dtype=np.int64), np.array([], dtype=np.float32))
-    return DocIndex(chunk_ids=np.concatenate(owners), embeddings=np.concatenate(blocks).astype(np.float32, copy=False))
+    pages = [pages_embeddings[_get_page_index(chunk)] for chunk in chunks]
+    return _flatten(pages, np.arange(len(pages)), np.float32)
 
 
 def create_index_by_chunk(chunks_embeddings: MultiEmbeddings | None) -> DocIndex:
     """Item i owns ``len(item.embeddings)`` consecutive rows (embeddings_index.py:121-136)."""
     if chunks_embeddings is None:
         return DocIndex()
-    owners, blocks = [], []
-    for i, item in enumerate(chunks_embeddings):
-        rows = _rows_of(item)
-        owners.append(np.full(len(rows), i, dtype=np.int64))
-        if len(rows):
-            blocks.append(rows.reshape(len(rows), -1))
-    if not blocks:
-        return DocIndex(np.array([], dtype=np.int64), np.array([], dtype=np.float32))
-    return DocIndex(chunk_ids=np.concatenate(owners), embeddings=np.concatenate(blocks))
+    matrix = _contiguous_matrix(chunks_embeddings)
+    if matrix is not None:   # n ordered [1, dim] views of one matrix: nothing to copy
+        return DocIndex(chunk_ids=np.arange(len(matrix), dtype=np.int64), embeddings=matrix)
+    return _flatten(chunks_embeddings, np.arange(len(chunks_embeddings)), None)
 
 
 def pack_multi_embeddings(indexes: List[int], embeddings: Iterable[np.ndarray], number_of_pages: int) -> MultiEmbeddings:
@@ -317,20 +388,28 @@ def pack_multi_embeddings(indexes: List[int], embeddings: Iterable[np.ndarray], 
     per_page: List[List[np.ndarray]] = [[] for _ in range(number_of_pages)]
     for page, emb in zip(indexes, embeddings, strict=True):
         per_page[page].append(emb)
-    return MultiEmbeddings(
-        [ItemEmbeddings(embeddings=to_ndarray(np.array(rows, dtype=np.float32))) for rows in per_page]
-    )
+    items = [ItemEmbeddings(embeddings=to_ndarray(np.array(rows, dtype=np.float32))) for rows in per_page]
+    if items:
+        items[0].id = _new_uid()
+    return MultiEmbeddings(items)
 
 
 def pack_simple_embeddings(embeddings: Iterable[np.ndarray]) -> MultiEmbeddings:
-    """One ``[1, dim]`` float32 array per chunk (embeddings_index.py:156-164)."""
-    return MultiEmbeddings(
-        [ItemEmbeddings(embeddings=to_ndarray(np.asarray(e, dtype=np.float32)[None, :])) for e in embeddings]
-    )
+    """One ``[1, dim]`` float32 array per chunk (embeddings_index.py:156-164).  The first item carries a build id
+    in its (persisted, otherwise unused) ``id`` field: the key of the device-resident index cache."""
+    items = [ItemEmbeddings(embeddings=to_ndarray(np.array([e], dtype=np.float32))) for e in embeddings]
+    if items:
+        items[0].id = _new_uid()
+    return MultiEmbeddings(items)
 
 
 def pack_embedding_matrix(matrix: np.ndarray) -> MultiEmbeddings:
-    """Zero-copy variant of ``pack_simple_embeddings`` for an ``[n, dim]`` float32 matrix:
-    every item is a ``[1, dim]`` view into ``matrix``."""
+    """Zero-copy variant of ``pack_simple_embeddings`` for an ``[n, dim]`` float32 matrix: every item is a
+    ``[1, dim]`` view into ``matrix``; ``create_index_by_chunk`` of the result is O(1)."""
     matrix = np.ascontiguousarray(matrix, dtype=np.float32)
-    return MultiEmbeddings([ItemEmbeddings(embeddings=to_ndarray(matrix[i : i + 1])) for i in range(len(matrix))])
+    items = [ItemEmbeddings(embeddings=to_ndarray(matrix[i : i + 1])) for i in range(len(matrix))]
+    if items:
+        items[0].id = _new_uid()
+    multi = MultiEmbeddings(items)
+    _remember_contiguous(multi, matrix)
+    return multi

@@ -44,6 +44,12 @@ except Exception:  # noqa: BLE001
         async def ainvoke(self, query: str, *args, **kwargs) -> List[Document]:
             return await self._aget_relevant_documents(query)
 
+        def batch(self, inputs: List[str], *args, **kwargs) -> List[List[Document]]:
+            return [self.invoke(q) for q in inputs]
+
+        async def abatch(self, inputs: List[str], *args, **kwargs) -> List[List[Document]]:
+            return list(await asyncio.gather(*(self.ainvoke(q) for q in inputs)))
+
 
 logger = logging.getLogger(__name__)
 
@@ -71,6 +77,23 @@ class SemanticRetriever(BaseRetriever):
     async def _aget_relevant_documents(self, query: str, *args, **kwargs) -> List[Document]:
         query_emb = np.array(await _emb.bge_embedding.aembed_query(query))
         return await asyncio.get_running_loop().run_in_executor(None, self._find_relevant_documents, query_emb)
+
+    # langchain's Runnable.batch / abatch fan a list of queries out to N single invocations (N forwards at batch 1 and
+    # N passes over the matrix).  Here: ONE packed forward for all queries, ONE find_batch (eval/eval_retriever.py:97 is
+    # the reference's caller).  Per-call callbacks/config of the Runnable protocol are not used on this path.
+    def batch(self, inputs: List[str], config: Any = None, **kwargs: Any) -> List[List[Document]]:
+        inputs = list(inputs)
+        if not inputs:
+            return []
+        queries = _emb.bge_embedding.embed_queries_numpy(inputs).astype(np.float64)
+        return self.index.find_batch(queries)
+
+    async def abatch(self, inputs: List[str], config: Any = None, **kwargs: Any) -> List[List[Document]]:
+        inputs = list(inputs)
+        if not inputs:
+            return []
+        queries = (await _emb.bge_embedding.aembed_queries_numpy(inputs)).astype(np.float64)
+        return await asyncio.get_running_loop().run_in_executor(None, self.index.find_batch, queries)
 
     @staticmethod
     async def build_index(chunks: List[Any], stageio=sys.stderr) -> MultiEmbeddings:

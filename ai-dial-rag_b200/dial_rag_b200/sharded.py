@@ -107,20 +107,34 @@ class ShardedIndex:
         return d, r, c
 
     # ---- exchange + merge --------------------------------------------------------
-    def topk(self, queries: np.ndarray, k: int, metric) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-        """Replicated queries in, identical global ``(dist, rows, count)`` out on every rank."""
+    def topk(self, queries: np.ndarray, k: int, metric, timers: Optional[dict] = None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """Replicated queries in, identical global ``(dist, rows, count)`` out on every rank.
+        ``timers`` (a dict, CUDA path only) receives the milliseconds of the call's stages -- local search (query
+        upload included), candidate packing, all-gather, merge, download -- from CUDA events on the current stream."""
         torch = self.torch
         queries = np.asarray(queries, dtype=np.float64)
         if queries.ndim == 1:
             queries = queries[None, :]
+        marks = []
+
+        def mark(name):
+            if timers is not None and self.comm_device.type == "cuda":
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(torch.cuda.current_stream(self.comm_device))
+                marks.append((name, ev))
+
+        mark("start")
         d, r, c = self._search_local(queries, k, metric)
+        mark("local_search")
         packed = pack_candidates(torch, d, r, c)
+        mark("pack")
         if self.world > 1:
             flat = torch.empty((self.world * packed.shape[0], packed.shape[1]), dtype=torch.int64, device=packed.device)
             self.dist.all_gather_into_tensor(flat, packed, group=self.group)  # ncclAllGather on GPUs
             gathered = flat.view(self.world, packed.shape[0], packed.shape[1])
         else:
             gathered = packed[None]
+        mark("all_gather")
         gd, gr, gc = unpack_candidates(torch, gathered, k)
         if self._merge is not None:
             md, mr, mc = self._merge(gd.numpy(), gr.numpy(), gc.numpy(), k)
@@ -129,7 +143,14 @@ class ShardedIndex:
         from dial_rag_b200.device_index import merge_topk_device
 
         md, mr, mc = merge_topk_device(_native.load(), self.comm_device.index, gd, gr, gc, k)
-        return md.cpu().numpy(), mr.cpu().numpy(), mc.cpu().numpy()
+        mark("merge")
+        out = md.cpu().numpy(), mr.cpu().numpy(), mc.cpu().numpy()
+        mark("download")
+        if marks:
+            torch.cuda.synchronize(self.comm_device)
+            for (_, a), (name, b) in zip(marks, marks[1:]):
+                timers[name] = timers.get(name, 0.0) + a.elapsed_time(b)
+        return out
 
 
 def embed_slice(encoder, token_lists: Sequence[Sequence[int]], rank: int, world: int) -> Tuple[np.ndarray, Tuple[int, int]]:

@@ -95,6 +95,19 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arms are meant to use every core the process may
+    run on (the N>=2 reference arm ran single-threaded)."""
+    import torch
+
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def synth_batches(n_batches: int, chunks: int, rank: int):
     from tests.synth import synth_token_batch
 
@@ -138,6 +151,7 @@ def time_cpu_baseline(weights, budget_s: float = 15.0, first: int = 32):
     from oracle import encoder as oenc
     from tests.synth import synth_token_batch
 
+    use_all_host_threads()
     embed, what = cpu_encoder(weights)
     ids, cu = synth_token_batch(seed=77, n_seq=first, seq_len=SEQ_LEN)
     lists = oenc.packed_to_lists(ids, cu)
@@ -164,6 +178,7 @@ def run_reference(args, rank: int):
     from oracle import encoder as oenc
     from tests.synth import synth_token_batch
 
+    use_all_host_threads()
     weights = oenc.synth_weights(seed=0, style="hf_init")
     embed, what = cpu_encoder(weights)
     sample = args.ref_chunks

@@ -15,9 +15,13 @@
  *     data_ptr()) and must stay valid until the work queued on `stream` is done;
  *     "h_" pointers are HOST pointers;
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
- *   - functions are re-entrant; an encoder object serialises its own callers with
- *     an internal lock (the reference's 1-worker pools may still issue an indexing
- *     and a query call at the same time, aidial_rag/resources/cpu_pools.py:50-59).
+ *   - functions are re-entrant.  An encoder object owns two activation workspaces,
+ *     a bulk one (max_tokens) and a small one for query-sized batches (<= 8192
+ *     tokens) with its own high-priority stream: an indexing call and a query
+ *     call (the reference's two 1-worker pools, aidial_rag/resources/cpu_pools.py:
+ *     50-59) run concurrently; calls that share a workspace are serialised -- host
+ *     threads by a lock, their GPU work by an event the next forward waits for
+ *     in-stream, whatever stream each caller passed.
  */
 #ifndef DRAG_B200_H_
 #define DRAG_B200_H_
@@ -118,8 +122,9 @@ int drag_encoder_forward_debug(drag_encoder* enc, const int32_t* d_ids, const in
 /*
  * Per-kernel-class device timing (CUDA events on the launch stream) for roofline reporting.
  * _begin arms up to max_launches event pairs; _end (after the caller synchronised the stream)
- * returns summed milliseconds and launch counts for the 7 classes
- *   {embed+LN, QKV GEMM, attention, out-proj GEMM+LN, FFN-up GEMM+GELU, FFN-down GEMM+LN, pool}.
+ * returns summed milliseconds and launch counts for the 8 classes
+ *   {embed+LN, QKV GEMM, attention, out-proj GEMM+LN, FFN-up GEMM+GELU, FFN-down GEMM+LN, pool,
+ *    CLS-only tail of the last layer}.  Only forwards in the bulk workspace are recorded.
  */
 int drag_encoder_profile_begin(drag_encoder* enc, int max_launches);
 int drag_encoder_profile_end(drag_encoder* enc, double* ms_by_class, int* launches_by_class);

@@ -81,7 +81,7 @@ def main() -> None:
 
     # ---- full bge-small-en shape, seeded weights
     recs = {}
-    for style, seed in (("hf_init", 0), ("stress", 7)):
+    for style, seed in (("hf_init", 0), ("stress", 7), ("outlier", 11)):
         w = enc.synth_weights(seed=seed, style=style)
         model = enc.hf_bert_model(w)
         ids, cu = synth_token_batch(seed=21, n_seq=10, seq_len=512, ragged=True, min_len=3)

@@ -33,6 +33,17 @@ def synth_weights(
     (HF ``_init_weights``).  ``stress``: same plus non-zero biases, random LN
     affine and 6x larger Q/K projections so that attention is peaked and every
     bias/affine code path changes the result -- a harder numerical target.
+    ``outlier``: ``stress`` plus what trained BERT checkpoints show and random init does
+    not: five hidden channels that carry 30x the magnitude of the rest in the residual
+    stream (embedding columns, the rows of both residual-producing projections and their
+    biases), LayerNorm gammas with outliers (4x on two of those channels, 0.25x on the other
+    three, 0.05 on a few ordinary channels) and LayerNorm betas with a common offset, so
+    that the residual stream has a non-zero mean.  As in trained models, the consumers
+    have learned to discount the massive channels (their Q/K/FFN-up weight columns are
+    30x smaller), which keeps the attention logits in a sane range: the model stays well
+    conditioned (HF's own fp16 path reproduces its fp32 output to cosine > 0.9999), so the
+    0.9995 bar is meaningful.  This is the case the folded LayerNorm (raw bf16 rows + fp32
+    sum / sum-of-squares) has to survive.
     """
     g = torch.Generator().manual_seed(seed)
     w: Dict[str, torch.Tensor] = {}
@@ -43,9 +54,16 @@ def synth_weights(
     def uniform(n, lo, hi):
         return torch.empty(n, dtype=torch.float32).uniform_(lo, hi, generator=g)
 
-    stress = style == "stress"
+    if style not in ("hf_init", "stress", "outlier"):
+        raise ValueError(f"unknown weight style {style!r}")
+    outlier = style == "outlier"
+    stress = style == "stress" or outlier
     h, f = shape.hidden, shape.inter
+    hot = [c % h for c in (7, 101, 250, 333, 380)]      # outlier channels
+    cold = [c % h for c in (19, 64, 200, 301)]          # channels with a tiny gamma
     w["embeddings.word_embeddings.weight"] = normal(shape.vocab, h)
+    if outlier:
+        w["embeddings.word_embeddings.weight"][:, hot] *= 30.0
     w["embeddings.word_embeddings.weight"][0].zero_()  # padding_idx=0
     w["embeddings.position_embeddings.weight"] = normal(shape.max_pos, h)
     w["embeddings.token_type_embeddings.weight"] = normal(shape.type_vocab, h)
@@ -53,6 +71,11 @@ def synth_weights(
     def ln(prefix):
         w[prefix + ".weight"] = uniform(h, 0.5, 1.5) if stress else torch.ones(h)
         w[prefix + ".bias"] = uniform(h, -0.3, 0.3) if stress else torch.zeros(h)
+        if outlier:
+            w[prefix + ".weight"][hot[:2]] *= 4.0
+            w[prefix + ".weight"][hot[2:]] *= 0.25
+            w[prefix + ".weight"][cold] = 0.05
+            w[prefix + ".bias"] += 0.4
 
     ln("embeddings.LayerNorm")
     for i in range(shape.layers):
@@ -70,6 +93,17 @@ def synth_weights(
                 std = 0.12
             w[p + lin + ".weight"] = normal(o, k, std=std)
             w[p + lin + ".bias"] = uniform(o, -0.1, 0.1) if stress else torch.zeros(o)
+            if outlier and lin in ("attention.output.dense", "output.dense"):
+                w[p + lin + ".weight"][hot] *= 30.0
+                w[p + lin + ".bias"][hot] += torch.tensor([2.0, -2.0, 1.5, -1.0, 2.5])
+            if outlier and lin in ("attention.self.query", "attention.self.key", "intermediate.dense"):
+                w[p + lin + ".weight"][:, hot] *= 1.0 / 30.0
         ln(p + "attention.output.LayerNorm")
         ln(p + "output.LayerNorm")
+    if outlier:
+        # the pooled embedding must not be carried by the massive channels alone (a cosine dominated by five
+        # coordinates would hide errors in the other 379): the last LayerNorm tames them
+        last = f"encoder.layer.{shape.layers - 1}.output.LayerNorm"
+        w[last + ".weight"][hot] = 0.02
+        w[last + ".bias"] = (w[last + ".bias"] - 0.4) * 0.1   # ... nor by a constant offset common to every input
     return w

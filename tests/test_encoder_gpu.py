@@ -96,7 +96,7 @@ def test_tcgen05_gemm_vs_torch(variant, N, K, M):
 
 @pytest.mark.parametrize("lens", [[1, 2, 17, 64, 65, 128, 256, 300, 512, 33], [512], [300, 77], [130] * 4],
                          ids=["ragged10", "one512", "two", "four130"])
-@pytest.mark.parametrize("variant", [2, 1, 0])
+@pytest.mark.parametrize("variant", [4, 3, 2, 1, 0])
 def test_attention_vs_torch(variant, lens):
     """Every attention kernel against torch fp32 softmax(QK^T/sqrt(32))V per packed sequence; the short
     batches exercise the 128- and 64-query tiles the mma.sync kernel picks when few sequences are in flight."""
@@ -123,12 +123,12 @@ def test_attention_vs_torch(variant, lens):
         assert err <= 0.03, (variant, n, err)
 
 
-@pytest.fixture(scope="module", params=["hf_init", "stress"])
+@pytest.fixture(scope="module", params=["hf_init", "stress", "outlier"])
 def model(request):
     from dial_rag_b200.embeddings.encoder import B200Encoder
 
     style = request.param
-    seed = {"hf_init": 0, "stress": 7}[style]
+    seed = {"hf_init": 0, "stress": 7, "outlier": 11}[style]
     w = oenc.synth_weights(seed=seed, style=style)
     enc = B200Encoder(w, device=0, max_tokens=16384)
     yield style, w, enc
@@ -165,7 +165,9 @@ def test_layer_taps_vs_oracle(model):
             assert c.min() >= (0.99999 if layer == 0 else 0.999), (style, layer, i, float(c.min()))
             # bf16 activations through `layer` layers; the stress weights (6x larger Q/K, random LN affine) put the
             # noise of the deepest tap right at 0.15, so that one gets headroom -- the contract metric is the cosine
-            assert np.abs(g - ref).max() <= {0: 0.03, 12: 0.25}.get(layer, 0.15), (style, layer, i)
+            # (the outlier weights carry hidden values of +-100: their bound scales with the magnitude)
+            slack = 0.006 * float(np.abs(ref).max()) if style == "outlier" else 0.0
+            assert np.abs(g - ref).max() <= {0: 0.03, 12: 0.25}.get(layer, 0.15) + slack, (style, layer, i)
 
 
 def test_embeddings_vs_hf_golden(model):

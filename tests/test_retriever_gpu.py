@@ -124,6 +124,71 @@ def test_resident_index_is_shared_between_requests(stack):
     RESIDENT_INDEXES.clear()
 
 
+def test_persisted_records_round_trip_and_hit_the_resident_index(stack):
+    """The reference persists a DocumentRecord as gzip(pickle(record)) (index_storage.py:44,156-165) and
+    DESERIALISES IT ON EVERY REQUEST (:136): what build_index returns must survive that format, feed
+    from_doc_records, give the same ranking -- and the second request must find the matrix already in HBM."""
+    import gzip
+    import pickle
+
+    emb, tok, w = stack
+    from dial_rag_b200.records import Chunk
+    from dial_rag_b200.retrievers.embeddings_index import RESIDENT_INDEXES
+    from dial_rag_b200.retrievers.semantic_retriever import SemanticRetriever
+
+    class Rec:   # picklable stand-in for the DocumentRecord fields on the path (document_record.py:42-52)
+        def __init__(self, embeddings_index, format_version=12):
+            self.embeddings_index = embeddings_index
+            self.format_version = format_version
+
+    RESIDENT_INDEXES.clear()
+    stored = []
+    live = []
+    for d in (CHUNKS[:12], CHUNKS[12:30]):
+        chunks = [Chunk(text=t, metadata={"chunk_id": i}) for i, t in enumerate(d)]
+        rec = Rec(asyncio.run(SemanticRetriever.build_index(chunks, io.StringIO())))
+        live.append(rec)
+        stored.append(gzip.compress(pickle.dumps(rec)))
+    in_process = SemanticRetriever.from_doc_records(live, k=7)
+    expected = [in_process._get_relevant_documents(q) for q in QUERIES]
+    hits0 = RESIDENT_INDEXES.hits
+    for request in range(3):   # every request deserialises afresh, like IndexStorage.load
+        records = [pickle.loads(gzip.decompress(b)) for b in stored]
+        assert records[0].embeddings_index is not live[0].embeddings_index
+        item = records[0].embeddings_index[0]
+        assert np.asarray(item.embeddings).dtype == np.float32 and np.asarray(item.embeddings).shape == (1, 384)
+        retriever = SemanticRetriever.from_doc_records(records, k=7)
+        assert retriever.index._matrix() is in_process.index._matrix()      # no re-flatten, no re-upload
+        assert [retriever._get_relevant_documents(q) for q in QUERIES] == expected
+    assert RESIDENT_INDEXES.hits - hits0 == 3 and len(RESIDENT_INDEXES) == 1
+    RESIDENT_INDEXES.clear()
+
+
+def test_retriever_batch_equals_single_calls(stack):
+    """SURVEY 8f-4 / eval/eval_retriever.py:97: ``batch`` / ``abatch`` embed all queries in ONE packed forward and
+    answer them with ONE ``find_batch``; results equal N single ``invoke`` calls."""
+    emb, tok, w = stack
+    from dial_rag_b200.records import Chunk
+    from dial_rag_b200.retrievers.semantic_retriever import SemanticRetriever
+
+    class Rec:
+        def __init__(self, embeddings_index):
+            self.embeddings_index = embeddings_index
+
+    chunks = [Chunk(text=t, metadata={"chunk_id": i}) for i, t in enumerate(CHUNKS)]
+    rec = Rec(asyncio.run(SemanticRetriever.build_index(chunks, io.StringIO())))
+    retriever = SemanticRetriever.from_doc_records([rec], k=5)
+    queries = QUERIES + [QUERIES[0], "multi\nline question about glaciers?"]
+    single = [retriever.invoke(q) for q in queries]
+    assert retriever.batch(queries) == single
+    assert asyncio.run(retriever.abatch(queries)) == single
+    assert retriever.batch([]) == [] and asyncio.run(retriever.abatch([])) == []
+    # the query embeddings of the batched call are the single-call embeddings, bit for bit
+    many = emb.bge_embedding_impl().embed_queries_numpy(queries)
+    for i, q in enumerate(queries):
+        assert np.array_equal(many[i].astype(np.float64), np.array(emb.bge_embedding.embed_query(q)))
+
+
 def test_embeddings_surface(stack):
     emb, tok, w = stack
     assert emb.EMBEDDING_LENGTH == 384
