@@ -89,10 +89,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if jobs or not os.path.exists(LIB):
         # the driver API (cuTensorMapEncodeTiled) is resolved at run time through
         # cudaGetDriverEntryPoint, so libcuda is not a link-time dependency
-        cmd = [nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        tmp = LIB + ".tmp"   # link next to the target, then rename: a repo snapshot never sees a half-written library
+        cmd = [nvcc(), "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        os.replace(tmp, LIB)
     return LIB
 
 

@@ -5,13 +5,15 @@
 // so the kernel is arranged around ONE rule: a softmax warp never waits for anything another softmax warp of
 // the other group could be computing exponentials behind.
 //
-// Persistent kernel, one CTA per SM, 10 working warps (12 launched: register budgets are set per warpgroup):
+// Persistent kernel, one CTA per SM, 11 working warps (12 launched: register budgets are set per warpgroup):
 //   warps 0-3   softmax group 0        thread = one query row of the group's current 128-query job
 //   warps 4-7   softmax group 1        (jobs alternate between the groups: the two run out of phase)
 //   warp  8     TMA producer: Q, K and V tiles (128 tokens x one head, 64-byte swizzle) of the next units
 //               straight out of the packed [T, 3*hidden] QKV buffer into a 1..4-stage ring
-//   warp  9     MMA issuer (one thread), POLLING the barriers it serves (mbarrier.test_wait), so the
-//               groups never wait for each other's tiles whatever the sequence lengths are
+//   warps 9,10  MMA issuers, one per softmax group, so the groups never wait for each other's tiles whatever the
+//               sequence lengths are.  The whole warp walks the job sequence (warp-uniform values: descriptors live
+//               in uniform registers) and one elected lane issues -- a P V step is only 16 clocks of tensor work, so
+//               the cost of ISSUING a tcgen05.mma matters here
 // The producer publishes a small descriptor of every unit next to its ring stage: the issuer and the softmax
 // warps walk the job sequence on shared memory only (a walker on global loads stalled the issuer for
 // thousands of cycles per job).
@@ -47,7 +49,7 @@ constexpr int QKV_TILE_BYTES = TILE * HEAD_DIM * 2;     // 8 KB: [128][32] bf16,
 constexpr int GROUPS = 2;
 constexpr int SOFTMAX_WARPS = 4 * GROUPS;
 constexpr int TMA_WARP = SOFTMAX_WARPS;
-constexpr int MMA_WARP = TMA_WARP + 1;
+constexpr int MMA_WARP = TMA_WARP + 1;                  // issuer of group 0; MMA_WARP + 1: group 1
 constexpr int THREADS = 384;                            // 3 warpgroups: softmax 0, softmax 1, {TMA, MMA, two idle warps}
 constexpr int SOFTMAX_REGS = 200;                       // setmaxnreg: 8 x 32 x 200 + 4 x 32 x 104 = 64 512 = 384 x 168
 constexpr int OTHER_REGS = 104;
@@ -135,7 +137,30 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
-// non-blocking probe (the issuer polls several barriers; try_wait may suspend the thread)
+// 2^x for a pair on the FMA / ALU pipes instead of the MUFU pipe (16 ex2 per clock per SM is what bounds this kernel):
+// x = j + f with j = round(x) (magic-number add), 2^f for f in [-0.5, 0.5] by a degree-3 polynomial (relative error 1.0e-4,
+// a twentieth of the bf16 rounding the weight gets next), then j goes straight into the exponent field.  Valid for
+// x in [-126, 127): smaller arguments are clamped (2^-126 is as good as 0 for a softmax weight).
+__device__ __forceinline__ void exp2_poly_pair(uint64_t x2, float& p0, float& p1) {
+  float x0, x1;
+  unpack_f32x2(x2, x0, x1);
+  x0 = fmaxf(x0, -126.f);
+  x1 = fmaxf(x1, -126.f);
+  const uint64_t xc = pack_f32x2(x0, x1);
+  const uint64_t t2 = add_f32x2(xc, pack_f32x2(12582912.f, 12582912.f));          // 1.5 * 2^23: j in the low mantissa bits
+  const uint64_t j2 = add_f32x2(t2, pack_f32x2(-12582912.f, -12582912.f));
+  const uint64_t f2 = fma_f32x2(j2, pack_f32x2(-1.f, -1.f), xc);
+  uint64_t q2 = fma_f32x2(f2, pack_f32x2(0.05500893f, 0.05500893f), pack_f32x2(0.24221095f, 0.24221095f));
+  q2 = fma_f32x2(q2, f2, pack_f32x2(0.6932829f, 0.6932829f));
+  q2 = fma_f32x2(q2, f2, pack_f32x2(1.f, 1.f));
+  float t0, t1, q0, q1;
+  unpack_f32x2(t2, t0, t1);
+  unpack_f32x2(q2, q0, q1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+
+// non-blocking probe (try_wait may suspend the thread)
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -159,8 +184,6 @@ struct UnitDesc {
   int S;           // sequence length
   int head;
   int part;        // first query tile of the unit (then part + split, ...)
-  int remaining;   // P V operations the unit still waits for (touched by the issuer only after publication)
-  int pad[3];
 };
 
 // The CTA's jobs in a fixed order: its units in ring order, per unit the query tiles part, part + split, ...; job ordinal
@@ -180,41 +203,56 @@ struct Cursor {
   int it = 0;        // ordinal of the unit (-> ring stage it % n_stages, phase it / n_stages; descriptor it % DESC_RING)
   int job = -1;      // CTA-wide job ordinal of the current job
   int qt = 0, n_tiles = 0, S = 0, tok0 = 0, head = 0;
-  bool have_unit = false, ready = false, done = false;
-  // Moves to the next job of group g.  BLOCKING = false: returns false when the next unit's descriptor has not been
-  // published yet (call again later); otherwise returns true with `ready` (a job) or `done` (end of stream) set.
-  template <bool BLOCKING>
-  __device__ __forceinline__ bool seek(int g, int split, const int* published, const UnitDesc* desc) {
-    ready = false;
+  bool have_unit = false, mine = false, done = false;
+  // Moves to the next job of group g; `done` is set at the end of the stream.  BLOCKING: waits for the descriptors it
+  // needs and returns true; otherwise returns false as soon as the next descriptor has not been published yet (the cursor
+  // keeps its position: call again later).  on_skip(it) is called for every unit the cursor leaves without having found
+  // a job of its group in it.  UNIFORM (whole-warp callers): decisions are taken for the warp as one and the descriptor
+  // fields go through a warp broadcast, which makes them (and everything computed from them) warp-uniform for the compiler.
+  template <bool UNIFORM, bool BLOCKING, typename OnSkip>
+  __device__ __forceinline__ bool seek(int g, int split, const int* published, const UnitDesc* desc, OnSkip on_skip) {
     for (;;) {
       if (!have_unit) {
         if (BLOCKING) {
           const long long t0 = clock64();
           while (ld_acquire_shared(published) <= it)
             if (clock64() - t0 > 4000000000ll) { printf("drag_b200: attention unit descriptor wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x); __trap(); }
-        } else if (ld_acquire_shared(published) <= it) {
-          return false;
+          if (UNIFORM) __syncwarp();
+        } else {
+          bool there = ld_acquire_shared(published) > it;
+          if (UNIFORM) there = __all_sync(0xffffffffu, there);
+          if (!there) return false;
         }
         const UnitDesc& d = desc[it % DESC_RING];
-        S = d.S;
+        S = d.S; tok0 = d.tok0; head = d.head;
+        int part = d.part;
+        if (UNIFORM) { S = __shfl_sync(0xffffffffu, S, 0); part = __shfl_sync(0xffffffffu, part, 0); }
         if (S == 0) { done = true; return true; }
-        tok0 = d.tok0; head = d.head;
         n_tiles = (S + TILE - 1) / TILE;
-        qt = d.part - split;
+        qt = part - split;
         have_unit = true;
+        mine = false;
       }
       qt += split;
-      if (qt >= n_tiles) { have_unit = false; ++it; continue; }
+      if (qt >= n_tiles) {
+        if (!mine) on_skip(it);
+        have_unit = false;
+        ++it;
+        continue;
+      }
       ++job;
-      if ((job & 1) == g) { ready = true; return true; }
+      if ((job & 1) == g) { mine = true; return true; }
     }
   }
+  // does the group have another job in the current unit after this one?
+  __device__ __forceinline__ bool last_of_group_in_unit(int split) const { return qt + 2 * split >= n_tiles; }
 };
 
 // qkv : [T, 3*hidden] bf16 (tensor map: box 32 columns x 128 rows, 64-byte swizzle)
 // ctx : [T, hidden] bf16
 // grid = min(#SMs, units), block = THREADS, dynamic smem = smem_bytes(longest sequence, P_BUFS)
-template <int P_BUFS>
+// POLY: every POLY-th pair of weights is computed by exp2_poly_pair instead of MUFU.EX2 (0 = none, 4 = 25 %, 2 = 50 %)
+template <int P_BUFS, int POLY>
 __global__ void __launch_bounds__(THREADS, 1)
 attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ ctx,
                      const int* __restrict__ cu_seqlens, int n_seq, int heads, int max_tiles, int n_stages, int split,
@@ -237,6 +275,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
   int* published = reinterpret_cast<int*>(tmem_ptr_smem + 1);        // descriptors written so far
   UnitDesc* desc = reinterpret_cast<UnitDesc*>(tmem_ptr_smem + 2);   // [DESC_RING]
   static_assert((2 * MAX_STAGES + 6 * GROUPS) * 8 + 8 + DESC_RING * sizeof(UnitDesc) <= BAR_BYTES, "barrier region too small");
+  auto no_skip = [](int) {};
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -247,7 +286,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
       tc::tma_prefetch_desc(&tmap_qkv);
       for (int s = 0; s < MAX_STAGES; ++s) {
         tc::mbar_init(&kv_full[s], 1);
-        tc::mbar_init(&kv_empty[s], 1);
+        tc::mbar_init(&kv_empty[s], GROUPS);   // one arrival per issuer: after its last P V in the unit, or on passing a unit without a job of its group
       }
       for (int g = 0; g < GROUPS; ++g) {
         tc::mbar_init(&s_full[g], 1);
@@ -275,7 +314,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(OTHER_REGS));
    if (warp == TMA_WARP) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       int stage = 0, it = 0;
       uint32_t phase = 0;
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -288,7 +327,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
         const int n_q = (n_tiles - part + split - 1) / split;
         tc::mbar_wait(&kv_empty[stage], phase ^ 1);
         UnitDesc& d = desc[it % DESC_RING];
-        d.tok0 = tok0; d.S = S; d.head = head; d.part = part; d.remaining = n_q * n_tiles;
+        d.tok0 = tok0; d.S = S; d.head = head; d.part = part;
         st_release_shared(published, ++it);
         uint8_t* base = smem + (size_t)stage * stage_bytes;
         tc::mbar_arrive_expect_tx(&kv_full[stage], (uint32_t)((n_q + 2 * n_tiles) * QKV_TILE_BYTES));
@@ -308,62 +347,91 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
       st_release_shared(published, ++it);
     }
     __syncwarp();
-   } else if (warp == MMA_WARP) {
-    // ===================== MMA issuer: polls  s_free / p_full  of both groups =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = idesc_bf16(TILE, TILE, false);
-      constexpr uint32_t idesc_o = idesc_bf16(TILE, HEAD_DIM, true);
-      Cursor qk[GROUPS], pv[GROUPS];
-      int qk_b[GROUPS] = {0, 0}, pv_b[GROUPS] = {0, 0};
-      uint32_t n_qk[GROUPS] = {0, 0}, n_pv[GROUPS] = {0, 0};
-      while (!(pv[0].done && pv[1].done)) {
-        // the four probes are independent: in flight together
-        bool sf[GROUPS], pf[GROUPS];
+   } else if (warp == MMA_WARP || warp == MMA_WARP + 1) {
+    // ===================== MMA issuer of group g:  S(0) | { S(n+1), P(n) V } ... =====================
+    // Per group the events alternate strictly -- s_free(n) (the scores of block n are in registers) precedes p_full(n) --
+    // so blocking waits in that order never stall the other group, which has its own issuer.  The next block's scores
+    // are issued BEFORE P(n) V unless their unit has not landed yet (its ring stage may be waiting for this very P V).
+    const int g = warp - MMA_WARP;
+    constexpr uint32_t idesc_s = idesc_bf16(TILE, TILE, false);
+    constexpr uint32_t idesc_o = idesc_bf16(TILE, HEAD_DIM, true);
+    const uint32_t smem_base = tc::smem_u32(smem);
+    const uint32_t p_base0 = tc::smem_u32(p_smem) + (uint32_t)(g * P_BUFS * P_BYTES);
+    // (all lanes run the control flow; one elected lane issues)
+    Cursor qk, pv;
+    int qk_b = 0, pv_b = 0;
+    uint32_t n_qk = 0, n_pv = 0;
+    bool qk_ready = false;   // qk points at a block whose scores have not been issued yet
+    // a unit passed without a job of this group: its ring stage does not wait for this issuer
+    auto skip_unit = [&](int it) { if (lane == 0) tc::mbar_arrive(&kv_empty[it % n_stages]); };
+    auto landed = [&](int it) { return __all_sync(0xffffffffu, mbar_test(&kv_full[it % n_stages], (uint32_t)(it / n_stages) & 1)); };
+    auto issue_scores = [&]() {
+      const int stage = qk.it % n_stages;
+      tc::mbar_wait(&kv_full[stage], (uint32_t)(qk.it / n_stages) & 1);
+      tc::mbar_wait(&s_free[g], (n_qk & 1) ^ 1);
+      tc::tc_fence_after();
+      const uint32_t base = smem_base + (uint32_t)stage * (uint32_t)stage_bytes;
+      const uint64_t q_desc = desc_k_sw64(base + (uint32_t)(qk.qt * QKV_TILE_BYTES));
+      const uint64_t k_desc = desc_k_sw64(base + (uint32_t)((max_tiles + qk_b) * QKV_TILE_BYTES));
+      __syncwarp();
+      if (tc::elect_one()) {
 #pragma unroll
-        for (int g = 0; g < GROUPS; ++g) {
-          sf[g] = mbar_test(&s_free[g], (n_qk[g] & 1) ^ 1);
-          pf[g] = mbar_test(&p_full[2 * g + (int)(n_pv[g] % P_BUFS)], (n_pv[g] / P_BUFS) & 1);
-        }
+        for (int k = 0; k < HEAD_DIM / 16; ++k)
+          tc::umma_bf16(tmem_base + g * TILE, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc_s, k != 0 ? 1u : 0u);
+        tc::umma_commit(&s_full[g]);
+      }
+      __syncwarp();
+      ++n_qk;
+      if (++qk_b == qk.n_tiles) { qk_b = 0; qk_ready = false; }   // the next job is looked up when its turn comes
+    };
+    auto issue_pv = [&]() {
+      const int stage = pv.it % n_stages;
+      const int buf = (int)(n_pv % P_BUFS);
+      tc::mbar_wait(&p_full[2 * g + buf], (n_pv / P_BUFS) & 1);
+      tc::tc_fence_after();
+      const uint32_t base = smem_base + (uint32_t)stage * (uint32_t)stage_bytes;
+      // +16 keys: 32 bytes inside P's 128-byte swizzle row (4 steps per 64-key atom), 1024 bytes down V's rows
+      const uint64_t a_desc = tc::umma_desc_sw128(p_base0 + (uint32_t)(buf * P_BYTES));
+      const uint64_t b_desc = desc_mn_sw64(base + (uint32_t)((2 * max_tiles + pv_b) * QKV_TILE_BYTES));
+      const bool last_in_job = pv_b + 1 == pv.n_tiles;
+      const bool release = last_in_job && pv.last_of_group_in_unit(split);
+      __syncwarp();
+      if (tc::elect_one()) {
 #pragma unroll
-        for (int g = 0; g < GROUPS; ++g) {
-          if (!qk[g].done) {
-            if (!qk[g].ready) qk[g].template seek<false>(g, split, published, desc);
-            if (qk[g].ready && sf[g] && mbar_test(&kv_full[qk[g].it % n_stages], (uint32_t)(qk[g].it / n_stages) & 1)) {
-              const Cursor& w = qk[g];
-              tc::tc_fence_after();
-              const uint32_t base = tc::smem_u32(smem + (size_t)(w.it % n_stages) * stage_bytes);
-              const uint64_t q_desc = desc_k_sw64(base + (uint32_t)(w.qt * QKV_TILE_BYTES));
-              const uint64_t k_desc = desc_k_sw64(base + (uint32_t)((max_tiles + qk_b[g]) * QKV_TILE_BYTES));
-#pragma unroll
-              for (int k = 0; k < HEAD_DIM / 16; ++k)
-                tc::umma_bf16(tmem_base + g * TILE, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc_s, k != 0 ? 1u : 0u);
-              tc::umma_commit(&s_full[g]);
-              ++n_qk[g];
-              if (++qk_b[g] == w.n_tiles) { qk_b[g] = 0; qk[g].ready = false; }
-            }
-          }
-          if (!pv[g].done) {
-            if (!pv[g].ready) pv[g].template seek<false>(g, split, published, desc);
-            if (pv[g].ready && pf[g]) {
-              const Cursor& w = pv[g];
-              tc::tc_fence_after();
-              const int stage = w.it % n_stages;
-              const uint32_t base = tc::smem_u32(smem + (size_t)stage * stage_bytes);
-              const uint32_t v_base = base + (uint32_t)((2 * max_tiles + pv_b[g]) * QKV_TILE_BYTES);
-              const uint32_t p_base = tc::smem_u32(p_smem + (size_t)(g * P_BUFS + (int)(n_pv[g] % P_BUFS)) * P_BYTES);
-#pragma unroll
-              for (int kk = 0; kk < TILE / 16; ++kk) {
-                const uint64_t a_desc = tc::umma_desc_sw128(p_base + (uint32_t)((kk >> 2) * P_ATOM_BYTES)) + (uint64_t)((kk & 3) * 2);
-                const uint64_t b_desc = desc_mn_sw64(v_base + (uint32_t)(kk * 16 * 64));
-                tc::umma_bf16(tmem_base + O_COL + g * HEAD_DIM, a_desc, b_desc, idesc_o, (pv_b[g] | kk) != 0 ? 1u : 0u);
-              }
-              tc::umma_commit(&o_full[2 * g + (int)(n_pv[g] % P_BUFS)]);
-              ++n_pv[g];
-              if (--desc[w.it % DESC_RING].remaining == 0) tc::umma_commit(&kv_empty[stage]);   // every MMA that reads the unit's stage has been issued
-              if (++pv_b[g] == w.n_tiles) { pv_b[g] = 0; pv[g].ready = false; }
-            }
-          }
-        }
+        for (int kk = 0; kk < TILE / 16; ++kk)
+          tc::umma_bf16(tmem_base + O_COL + g * HEAD_DIM, a_desc + (uint64_t)((kk >> 2) * (P_ATOM_BYTES >> 4) + (kk & 3) * 2),
+                        b_desc + (uint64_t)(kk * (1024 >> 4)), idesc_o, (pv_b | kk) != 0 ? 1u : 0u);
+        tc::umma_commit(&o_full[2 * g + buf]);
+        if (release) tc::umma_commit(&kv_empty[stage]);   // every MMA of this group that reads the unit's stage has been issued
+      }
+      __syncwarp();
+      ++n_pv;
+      if (last_in_job) {
+        pv_b = 0;
+        // Blocking is safe here: everything this group owes the current unit has been issued, so the unit's stage
+        // (which the next descriptor may be waiting for) is released by the other group's issuer alone.
+        pv.template seek<true, true>(g, split, published, desc, skip_unit);
+      } else {
+        ++pv_b;
+      }
+    };
+    pv.template seek<true, true>(g, split, published, desc, skip_unit);   // (units passed on the way are released at once)
+    qk = pv;
+    qk_ready = !qk.done;
+    if (qk_ready) issue_scores();
+    while (!pv.done) {
+      // the scores of the next block go out BEFORE P(n) V -- unless their unit (or even its descriptor) is not there yet:
+      // with a full ring it is waiting for this very P V
+      if (!qk_ready && !qk.done) qk_ready = qk.template seek<true, false>(g, split, published, desc, no_skip) && !qk.done;
+      bool scored = false;
+      if (qk_ready && landed(qk.it)) {
+        issue_scores();
+        scored = true;
+      }
+      issue_pv();
+      if (!scored && !qk.done) {
+        if (!qk_ready) { qk.template seek<true, true>(g, split, published, desc, no_skip); qk_ready = !qk.done; }
+        if (qk_ready) issue_scores();
       }
     }
     __syncwarp();
@@ -382,7 +450,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
     // waits until P V of the group's block n has retired (the MMAs retire in order: so have all earlier ones)
     auto wait_pv = [&](uint32_t n) { tc::mbar_wait(&o_full[2 * g + (int)(n % P_BUFS)], (n / P_BUFS) & 1); };
     Cursor w;
-    while (w.template seek<true>(g, split, published, desc), !w.done) {
+    while (w.template seek<false, true>(g, split, published, desc, no_skip), !w.done) {
       float m = -INFINITY, l = 0.f;
       for (int b = 0; b < w.n_tiles; ++b, ++k) {
         const int valid = w.S - b * TILE;            // keys of this block inside the sequence (>= 1)
@@ -426,9 +494,20 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
 #pragma unroll
         for (int i = 0; i < TILE; i += 4) {
           float p0, p1, p2, p3;
-          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), scale2, noff2), p0, p1);
-          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), scale2, noff2), p2, p3);
-          p0 = ex2(p0); p1 = ex2(p1); p2 = ex2(p2); p3 = ex2(p3);
+          const uint64_t xa = fma_f32x2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), scale2, noff2);
+          const uint64_t xb = fma_f32x2(pack_f32x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), scale2, noff2);
+          if (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == 0) {
+            exp2_poly_pair(xa, p0, p1);
+          } else {
+            unpack_f32x2(xa, p0, p1);
+            p0 = ex2(p0); p1 = ex2(p1);
+          }
+          if (POLY > 0 && (((i >> 1) + 1) % (POLY > 0 ? POLY : 1)) == 0) {
+            exp2_poly_pair(xb, p2, p3);
+          } else {
+            unpack_f32x2(xb, p2, p3);
+            p2 = ex2(p2); p3 = ex2(p3);
+          }
           l2a = add_f32x2(l2a, pack_f32x2(p0, p1));
           l2b = add_f32x2(l2b, pack_f32x2(p2, p3));
           pk[i >> 1] = pack2(p0, p1);

@@ -233,7 +233,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       if (WS && my_tiles > 0) {
@@ -272,7 +272,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && cta_rank == 0) {
+    if (cta_rank == 0 && tc::elect_one()) {
       const uint32_t idesc = p.f16_operands ? tc::umma_idesc_f16(TILE_M, BLOCK_N) : tc::umma_idesc_bf16(TILE_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
@@ -356,7 +356,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // RES: the warp's 32 x 64 box of raw residual rows arrives by TMA in the staging buffer the output
     // will be written to (same box, same swizzle: the epilogue works in place), one tile ahead
     auto fetch_residual = [&](int it_, int buf_) {
-      if (lane == 0) {
+      if (tc::elect_one()) {
         tc::mbar_arrive_expect_tx(&res_bar[2 * ew + buf_], STAGING_BYTES);
         tc::tma_load_2d(&tmap_res, &res_bar[2 * ew + buf_], stage_buf + (size_t)buf_ * STAGING_BYTES, tile_n(it_) * BLOCK_N + col_group * COLS_PER_THREAD,
                         tile_m(it_) * TILE_M + (int)cta_rank * BLOCK_M + quarter * 32);
@@ -501,7 +501,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (half == 1) {
           tc::fence_proxy_async();
           __syncwarp();
-          if (lane == 0 && !(p.dbg & 1)) {
+          if (!(p.dbg & 1) && tc::elect_one()) {
             tc::tma_store_2d(&tmap_out, stage_buf + (size_t)sbuf * STAGING_BYTES, col0 + c - 32, ((p.dbg & 4) ? (int)(blockIdx.x & 1) * BLOCK_M : row0) + quarter * 32);
             tc::tma_store_commit();
           }

@@ -117,7 +117,7 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       // the query tile stays resident for the whole kernel
       tc::mbar_arrive_expect_tx(a_full_bar, (uint32_t)(p.k_blocks * A_KB_BYTES));
       for (int kb = 0; kb < p.k_blocks; ++kb)
@@ -137,7 +137,7 @@ score_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       constexpr uint32_t idesc = tc::umma_idesc_bf16(QT, RT);
       tc::mbar_wait(a_full_bar, 0);
       tc::tc_fence_after();

@@ -207,12 +207,38 @@ class DeviceMatrix:
         more run the tensor-core candidate pass + float64 re-rank (same results; synchronises once
         to read the per-query status).
         """
-        if not 1 <= k <= MAX_K:
-            raise DragError(3, f"k={k} outside the supported range 1..{MAX_K}")
+        if k < 1:
+            raise DragError(3, f"k={k} must be positive")
         code = _metric_code(metric)
+        if k > MAX_K:
+            # beyond the selection kernels' list size (the reference's argsort()[:limit] takes any limit,
+            # embeddings_index.py:57-59): every distance from drag_distances, then a stable device sort -- same order
+            # (ascending, NaN last, ties by row id), one full pass and a sort per query instead of a fused scan
+            return self._topk_sort_device(d_queries, k, code)
         if allow_batch and self._use_batch(int(d_queries.shape[0]), k, code):
             return self._topk_batch_device(d_queries, k, code)
         return self._topk_scan_device(d_queries, k, code)
+
+    def _topk_sort_device(self, d_queries, k: int, metric_code: int):
+        torch = _torch()
+        dev = self.matrix.device
+        nq = int(d_queries.shape[0])
+        k = min(k, self.n_rows)
+        dist = torch.empty((nq, k), dtype=torch.float64, device=dev)
+        rows = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        count = torch.full((nq,), k, dtype=torch.int32, device=dev)
+        full = torch.empty(self.n_rows, dtype=torch.float64, device=dev)
+        scratch = torch.empty(2, dtype=torch.float64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        for i in range(nq):
+            with torch.cuda.device(dev):
+                _native.check(
+                    self.lib.drag_distances(self.device, _ptr(self.matrix), self.dtype_code, self.n_rows, self.dim,
+                                            _ptr(self.row_sq), _ptr(d_queries[i]), metric_code, _ptr(full), _ptr(scratch), stream)
+                )
+            vals, idx = torch.sort(full, stable=True)   # NaN sorts last, like np.argsort
+            dist[i], rows[i] = vals[:k], idx[:k] + self.row_id_base
+        return dist, rows, count
 
     def _topk_scan_device(self, d_queries, k: int, metric_code: int):
         torch = _torch()

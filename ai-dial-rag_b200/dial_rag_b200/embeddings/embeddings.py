@@ -35,7 +35,11 @@ from dial_rag_b200.batched import TqdmProgressBar, batched_map_with_progress, ch
 from dial_rag_b200.embeddings.detect_device import DeviceType, detect_device
 from dial_rag_b200.embeddings.encoder import BGE_SMALL, B200Encoder, EncoderShape, load_model_dir
 from dial_rag_b200.embeddings.tokenizer import WordPieceTokenizer
-from dial_rag_b200.resources.cpu_pools import run_in_indexing_embeddings_pool, run_in_query_embeddings_pool
+from dial_rag_b200.resources.cpu_pools import (
+    run_in_indexing_cpu_pool,
+    run_in_indexing_embeddings_pool,
+    run_in_query_embeddings_pool,
+)
 
 try:  # use langchain's base class when the package lives inside a Dial RAG deployment
     from langchain.schema.embeddings import Embeddings  # type: ignore
@@ -85,9 +89,9 @@ class B200BgeEmbeddings(Embeddings):
     def from_model_dir(cls, path: str, device: int = 0, **kw) -> "B200BgeEmbeddings":
         return cls(load_model_dir(path), WordPieceTokenizer.from_model_dir(path), device=device, **kw)
 
-    def tokenize_documents(self, texts: Sequence[str]):
+    def tokenize_documents(self, texts: Sequence[str], n_threads: int = 0):
         """Host half of ``embed_documents``: text preparation + WordPiece -> packed ``(ids, cu_seqlens)``."""
-        return self.tokenizer.encode_packed([self.embed_instruction + t.replace("\n", " ") for t in texts])
+        return self.tokenizer.encode_packed([self.embed_instruction + t.replace("\n", " ") for t in texts], n_threads=n_threads)
 
     def embed_packed_numpy(self, ids: np.ndarray, cu_seqlens: np.ndarray) -> np.ndarray:
         """Device half: packed ids -> float32 ``[n, 384]`` on the host."""
@@ -172,20 +176,37 @@ class AsyncEmbeddings(Embeddings):
 bge_embedding = AsyncEmbeddings()
 
 
+# host threads one tokenisation call may use (several indexing requests can be in flight: the reference bounds its
+# CPU work with the indexing pool, resources/cpu_pools.py:37-59)
+TOKENIZER_THREADS = int(os.environ.get("DIAL_RAG_B200_TOKENIZER_THREADS", str(max(1, min(8, (os.cpu_count() or 2) // 2)))))
+
+
 async def build_embeddings(texts: Iterable[str], stageio):
     """Embed ``texts`` in order, batch by batch, with progress lines (embeddings.py:102-108).
 
     Same contract as the reference (ordered results, ONE batch at a time on the indexing-embeddings worker,
-    tqdm keep-alive lines); the only addition is that batch i+1 is tokenised on the loop's default executor
-    while batch i is on the GPU, so the host half never leaves the device idle."""
+    tqdm keep-alive lines); the only addition is that batch i+1 is tokenised -- on the bounded indexing CPU pool, with a
+    bounded thread count -- while batch i is on the GPU, so the host half never leaves the device idle."""
     impl = bge_embedding_impl()
-    loop = asyncio.get_running_loop()
     batches = list(chunked(texts, EMBEDDINGS_BATCH_SIZE))
     results = []
-    ahead = loop.run_in_executor(None, impl.tokenize_documents, batches[0]) if batches else None
-    for i, _ in enumerate(TqdmProgressBar(iterable=batches, file=stageio)):
-        ids, cu = await ahead
-        ahead = loop.run_in_executor(None, impl.tokenize_documents, batches[i + 1]) if i + 1 < len(batches) else None
-        matrix = await run_in_indexing_embeddings_pool(impl.embed_packed_numpy, ids, cu)   # strictly one batch in flight
-        results.append(list(matrix))  # float32 row views, shape (384,)
+
+    def tokenize(batch):
+        return impl.tokenize_documents(batch, n_threads=TOKENIZER_THREADS)
+
+    ahead = asyncio.ensure_future(run_in_indexing_cpu_pool(tokenize, batches[0])) if batches else None
+    try:
+        for i, _ in enumerate(TqdmProgressBar(iterable=batches, file=stageio)):
+            ids, cu = await ahead
+            ahead = asyncio.ensure_future(run_in_indexing_cpu_pool(tokenize, batches[i + 1])) if i + 1 < len(batches) else None
+            matrix = await run_in_indexing_embeddings_pool(impl.embed_packed_numpy, ids, cu)   # strictly one batch in flight
+            results.append(list(matrix))  # float32 row views, shape (384,)
+    finally:
+        if ahead is not None and not ahead.done():
+            ahead.cancel()
+        if ahead is not None:
+            try:
+                await ahead        # retrieve the outcome: no "exception was never retrieved", no stray work
+            except BaseException:  # noqa: BLE001 - cancelled, or failed after the batch that raised
+                pass
     return chain.from_iterable(results)

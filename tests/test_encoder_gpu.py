@@ -96,7 +96,7 @@ def test_tcgen05_gemm_vs_torch(variant, N, K, M):
 
 @pytest.mark.parametrize("lens", [[1, 2, 17, 64, 65, 128, 256, 300, 512, 33], [512], [300, 77], [130] * 4],
                          ids=["ragged10", "one512", "two", "four130"])
-@pytest.mark.parametrize("variant", [4, 3, 2, 1, 0])
+@pytest.mark.parametrize("variant", [6, 5, 4, 3, 2, 1, 0])
 def test_attention_vs_torch(variant, lens):
     """Every attention kernel against torch fp32 softmax(QK^T/sqrt(32))V per packed sequence; the short
     batches exercise the 128- and 64-query tiles the mma.sync kernel picks when few sequences are in flight."""
@@ -165,9 +165,10 @@ def test_layer_taps_vs_oracle(model):
             assert c.min() >= (0.99999 if layer == 0 else 0.999), (style, layer, i, float(c.min()))
             # bf16 activations through `layer` layers; the stress weights (6x larger Q/K, random LN affine) put the
             # noise of the deepest tap right at 0.15, so that one gets headroom -- the contract metric is the cosine
-            # (the outlier weights carry hidden values of +-100: their bound scales with the magnitude)
-            slack = 0.006 * float(np.abs(ref).max()) if style == "outlier" else 0.0
-            assert np.abs(g - ref).max() <= {0: 0.03, 12: 0.25}.get(layer, 0.15) + slack, (style, layer, i)
+            # (the outlier weights carry hidden values of +-100, where one bf16 ulp is 0.5: their bound is element-wise
+            # relative -- 2 % of the value, five bf16 ulps -- on top of the absolute one)
+            slack = 0.02 * np.abs(ref) if style == "outlier" else 0.0
+            assert (np.abs(g - ref) <= {0: 0.03, 12: 0.25}.get(layer, 0.15) + slack).all(), (style, layer, i)
 
 
 def test_embeddings_vs_hf_golden(model):

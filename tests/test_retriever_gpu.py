@@ -16,6 +16,14 @@ from tests.text_fixture import CHUNKS, QUERIES, build_vocab_file
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 
 
+class StoredRecord:
+    """Picklable stand-in for the DocumentRecord fields on the path (document_record.py:42-52)."""
+
+    def __init__(self, embeddings_index, format_version=12):
+        self.embeddings_index = embeddings_index
+        self.format_version = format_version
+
+
 @pytest.fixture(scope="module")
 def stack(tmp_path_factory):
     from dial_rag_b200.embeddings import embeddings as emb
@@ -136,11 +144,7 @@ def test_persisted_records_round_trip_and_hit_the_resident_index(stack):
     from dial_rag_b200.retrievers.embeddings_index import RESIDENT_INDEXES
     from dial_rag_b200.retrievers.semantic_retriever import SemanticRetriever
 
-    class Rec:   # picklable stand-in for the DocumentRecord fields on the path (document_record.py:42-52)
-        def __init__(self, embeddings_index, format_version=12):
-            self.embeddings_index = embeddings_index
-            self.format_version = format_version
-
+    Rec = StoredRecord
     RESIDENT_INDEXES.clear()
     stored = []
     live = []
@@ -187,6 +191,51 @@ def test_retriever_batch_equals_single_calls(stack):
     many = emb.bge_embedding_impl().embed_queries_numpy(queries)
     for i, q in enumerate(queries):
         assert np.array_equal(many[i].astype(np.float64), np.array(emb.bge_embedding.embed_query(q)))
+
+
+def test_config1_alps_wiki_corpus(tmp_path):
+    """BASELINE config 1 on the reference's own document (tests/data/alps_wiki.html, imported as text): index the 145
+    chunks through build_index, ask the reference test's question (tests/test_retrievers.py:90-92) and three more;
+    embeddings within cosine 0.9995 of the fp32 oracle, top-7 identical to the reference search over the same
+    embeddings, and the oracle's own top hit is what the CUDA path ranks first."""
+    from dial_rag_b200.embeddings import embeddings as emb
+    from dial_rag_b200.embeddings.tokenizer import WordPieceTokenizer
+    from dial_rag_b200.records import Chunk
+    from dial_rag_b200.retrievers.semantic_retriever import SemanticRetriever
+    from tests.text_fixture import ALPS_QUERIES, alps_wiki_chunks
+
+    texts = alps_wiki_chunks()
+    assert len(texts) == 145 and max(map(len, texts)) <= 1000
+    tok = WordPieceTokenizer.from_vocab_file(build_vocab_file(str(tmp_path), texts + ALPS_QUERIES))
+    w = oenc.synth_weights(seed=0, style="hf_init")
+    impl = emb.B200BgeEmbeddings(w, tok, device=0, max_tokens=65536)
+    emb.configure(impl)
+    try:
+        chunks = [Chunk(text=t, metadata={"chunk_id": i}) for i, t in enumerate(texts)]
+        rec = StoredRecord(asyncio.run(SemanticRetriever.build_index(chunks, io.StringIO())))
+        retriever = SemanticRetriever.from_doc_records([rec], k=7)
+        gpu = np.stack([np.asarray(item.embeddings)[0] for item in rec.embeddings_index])
+        ids = tok.encode_batch([oenc.prepare_document_text(t) for t in texts])
+        assert max(map(len, ids)) > 150          # real multi-hundred-token chunks, ragged
+        orc = oenc.encode_token_lists(w, ids)
+        cos = (gpu.astype(np.float64) * orc).sum(1) / (np.linalg.norm(gpu, axis=1) * np.linalg.norm(orc, axis=1))
+        assert cos.min() >= 0.9995, cos.min()
+        docs_gpu = [(np.arange(len(gpu), dtype=np.int64), gpu)]
+        for q in ALPS_QUERIES:
+            got = [(d.metadata["doc_id"], d.metadata["chunk_id"]) for d in retriever.invoke(q)]
+            q_gpu = np.asarray(emb.bge_embedding.embed_query(q), dtype=np.float64)
+            want = osearch.find("sqeuclidean_dist", 7, q_gpu, docs_gpu)
+            assert got == [(dd, c) for dd, c, _ in want], q
+            q_orc = oenc.encode_token_lists(w, tok.encode_batch([oenc.prepare_query_text(q)]))[0].astype(np.float64)
+            assert q_gpu @ q_orc >= 0.9995
+            best_orc = osearch.find("sqeuclidean_dist", 1, q_orc, [(np.arange(len(orc), dtype=np.int64), orc)])[0]
+            d_best = ((gpu[best_orc[1]].astype(np.float64) - q_gpu) ** 2).sum()
+            d_got = ((gpu[got[0][1]].astype(np.float64) - q_gpu) ** 2).sum()
+            assert got[0][1] == best_orc[1] or abs(d_best - d_got) <= 4e-3, (q, got[0], best_orc)
+        assert retriever.batch(ALPS_QUERIES) == [retriever.invoke(q) for q in ALPS_QUERIES]
+    finally:
+        emb.configure(None)
+        impl.client.close()
 
 
 def test_embeddings_surface(stack):

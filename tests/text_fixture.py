@@ -50,13 +50,33 @@ QUERIES = [
 ]
 
 
-def build_vocab_file(directory: str) -> str:
+def alps_wiki_chunks():
+    """BASELINE config 1 corpus: the text of the reference's own tests/data/alps_wiki.html in pieces of <= 1000
+    characters (fixture made by oracle/make_golden_alps.py; the real bge vocabulary is not available offline, so the
+    tests tokenise it with a deterministic WordPiece vocabulary built from the text itself)."""
+    import json
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "alps_wiki_chunks.json"), encoding="utf-8") as f:
+        return json.load(f)["chunks"]
+
+
+# the reference's own retriever test asks the first of these (tests/test_retrievers.py:90-92)
+ALPS_QUERIES = [
+    "what is the climate in the alps?",
+    "which is the highest mountain of the alps?",
+    "how were the alps formed?",
+    "which animals live in the alps?",
+]
+
+
+def build_vocab_file(directory: str, texts=None) -> str:
     words = set()
-    for text in CHUNKS + QUERIES + ["Represent this question for searching relevant passages: hello world a b"]:
+    corpus = CHUNKS + QUERIES if texts is None else list(texts)
+    for text in corpus + ["Represent this question for searching relevant passages: hello world a b"]:
         words.update(re.findall(r"[a-z]+|[^a-z\s]", text.lower()))
     vocab = ["[PAD]"] + [f"[unused{i}]" for i in range(99)] + ["[UNK]", "[CLS]", "[SEP]", "[MASK]"]
     letters = "abcdefghijklmnopqrstuvwxyz"
-    vocab += list(letters) + ["##" + c for c in letters] + list(".,:;?!'\"-()")
+    vocab += list(letters) + ["##" + c for c in letters] + list("0123456789") + ["##" + c for c in "0123456789"] + list(".,:;?!'\"-()")
     # only part of the words become whole tokens so that real word-piece splitting happens
     for w in sorted(words):
         if len(w) > 1 and (len(w) <= 5 or sum(map(ord, w)) % 3):
