@@ -25,12 +25,15 @@
 //                               handed back at once (the next block's scores are computed behind this block's
 //                               exponentials); row maximum, lazily raised reference m (only when a score
 //                               exceeds it by 2^8: the softmax is invariant to the reference), p = 2^(s c - m c)
-//                               on fp32 pairs (FFMA2 / FADD2), bf16 pairs into the group's P buffer (K-major,
-//                               128-byte swizzle: the A operand of P V)
-//   O[128 x 32] (+)= P V        tcgen05.mma M=128 N=32 K=16 x8 into TMEM columns [256 + 32 g, +32); V is
-//                               consumed as stored ([key][32]: an MN-major B operand).  O stays in TMEM across
-//                               the key blocks of a job; a raised reference rescales it in place (rare).
-//   end of job                  O / l -> bf16 -> ctx (rows inside the sequence only)
+//                               (FFMA2 + MUFU.EX2), bf16 pairs by TRUNCATION (one PRMT per pair: the F2FP
+//                               conversion runs at a third of the ALU rate, measured) into the group's P buffer
+//                               (K-major, 128-byte swizzle: the A operand of P V)
+//   O[128 x 32] (+)= P V        tcgen05.mma M=128 N=32 K=16 x8 into TMEM columns [256 + 48 g, +32); V is
+//   L[128 x 16] (+)= P 1        consumed as stored ([key][32]: an MN-major B operand); the row sums come out of the
+//                               tensor core over exactly the truncated weights of the numerator (the truncation
+//                               bias cancels in O / L, and the softmax loop carries no additions).  O and L stay
+//                               in TMEM across the key blocks of a job; a raised reference rescales them (rare).
+//   end of job                  O / L -> bf16 -> ctx (rows inside the sequence only)
 // Keys beyond the sequence do not exist in the packed layout: the tail of the last block is masked before the
 // row maximum.  Every row's result depends on that row's scores only (no cross-row decision), so it does not
 // depend on the batch composition.
@@ -54,7 +57,9 @@ constexpr int THREADS = 384;                            // 3 warpgroups: softmax
 constexpr int SOFTMAX_REGS = 200;                       // setmaxnreg: 8 x 32 x 200 + 4 x 32 x 104 = 64 512 = 384 x 168
 constexpr int OTHER_REGS = 104;
 constexpr int TMEM_COLS = 512;
-constexpr int O_COL = GROUPS * TILE;                    // group g: S at [128 g, +128), O at [256 + 32 g, +32)
+constexpr int O_COL = GROUPS * TILE;                    // group g: S at [128 g, +128), O at [256 + 48 g, +32), L at [256 + 48 g + 32, +16)
+constexpr int OL_COLS = HEAD_DIM + 16;                  // O and the row sums L = P . 1 (a 16-column MMA against a tile of ones)
+constexpr int ONES_BYTES = 1024;                        // [16][32] bf16 ones (all equal: layout and swizzle do not matter)
 constexpr int P_ATOM_BYTES = TILE * 64 * 2;             // 16 KB: [128 rows][64 keys] bf16, 128-byte swizzle
 constexpr int P_BYTES = 2 * P_ATOM_BYTES;               // one 128-key block of P
 constexpr int MAX_STAGES = 4;
@@ -64,12 +69,12 @@ constexpr float LAZY_LOG2 = 8.f;                        // numerators stay <= 2^
 
 __host__ __device__ inline int unit_stages(int max_len, int p_bufs) {
   const int tiles = (max_len + TILE - 1) / TILE;
-  const int fit = (SMEM_BUDGET - GROUPS * p_bufs * P_BYTES - 1024 - BAR_BYTES) / (3 * tiles * QKV_TILE_BYTES);
+  const int fit = (SMEM_BUDGET - GROUPS * p_bufs * P_BYTES - ONES_BYTES - 1024 - BAR_BYTES) / (3 * tiles * QKV_TILE_BYTES);
   return fit < 1 ? 1 : (fit < MAX_STAGES ? fit : MAX_STAGES);
 }
 __host__ __device__ inline size_t smem_bytes(int max_len, int p_bufs) {
   const int tiles = (max_len + TILE - 1) / TILE;
-  return (size_t)unit_stages(max_len, p_bufs) * 3 * tiles * QKV_TILE_BYTES + (size_t)GROUPS * p_bufs * P_BYTES + 1024 /*alignment*/ + BAR_BYTES;
+  return (size_t)unit_stages(max_len, p_bufs) * 3 * tiles * QKV_TILE_BYTES + (size_t)GROUPS * p_bufs * P_BYTES + ONES_BYTES + 1024 /*alignment*/ + BAR_BYTES;
 }
 // few items in flight (the query path): an item's query tiles are dealt to `split` units so that the launch fills the GPU
 __host__ __device__ inline int pick_split(int n_items, int max_len, int sms) {
@@ -173,6 +178,24 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15};"
+      ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(taddr)
+      : "memory");
+}
+// two non-negative fp32 -> bf16 pair by truncation (high halves): one PRMT
+__device__ __forceinline__ uint32_t trunc_bf16x2(float lo, float hi) { return __byte_perm(__float_as_uint(lo), __float_as_uint(hi), 0x7632); }
+
 // What the TMA producer publishes about every unit, in a ring of DESC_RING descriptors indexed by the unit's ordinal,
 // BEFORE it waits for the unit's data; `published` counts them.  S = 0 marks the end of the CTA's stream.
 // Jobs alternate between the groups, so a group's cursor passes over at most one unit without a job of its own before
@@ -251,8 +274,14 @@ struct Cursor {
 // qkv : [T, 3*hidden] bf16 (tensor map: box 32 columns x 128 rows, 64-byte swizzle)
 // ctx : [T, hidden] bf16
 // grid = min(#SMs, units), block = THREADS, dynamic smem = smem_bytes(longest sequence, P_BUFS)
+// Debug timeline (TRACE instantiation only, scripts/attn_trace.py): CTA 0 records clock64() at the phase boundaries of its
+// first TRACE_BLOCKS key blocks -- per softmax warp 8 stamps per block, per issuer 4 stamps per block.
+constexpr int TRACE_BLOCKS = 96;
+constexpr int TRACE_WORDS = SOFTMAX_WARPS * TRACE_BLOCKS * 8 + GROUPS * TRACE_BLOCKS * 4;
+__device__ long long* g_trace = nullptr;
+
 // POLY: every POLY-th pair of weights is computed by exp2_poly_pair instead of MUFU.EX2 (0 = none, 4 = 25 %, 2 = 50 %)
-template <int P_BUFS, int POLY>
+template <int P_BUFS, int POLY, bool TRACE = false>
 __global__ void __launch_bounds__(THREADS, 1)
 attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ ctx,
                      const int* __restrict__ cu_seqlens, int n_seq, int heads, int max_tiles, int n_stages, int split,
@@ -262,7 +291,8 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
   const int hidden = heads * HEAD_DIM;
   const size_t stage_bytes = (size_t)3 * max_tiles * QKV_TILE_BYTES;  // [Q tiles | K tiles | V tiles]
   uint8_t* p_smem = smem + (size_t)n_stages * stage_bytes;            // multiple of 8 KB: 1024-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + (size_t)GROUPS * P_BUFS * P_BYTES);
+  uint8_t* ones_smem = p_smem + (size_t)GROUPS * P_BUFS * P_BYTES;   // 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones_smem + ONES_BYTES);
   uint64_t* kv_full = bars;                    // [MAX_STAGES] TMA -> everybody: the unit (and its descriptor) has landed
   uint64_t* kv_empty = bars + MAX_STAGES;      // [MAX_STAGES] MMA -> TMA (every MMA that reads the unit has retired)
   uint64_t* s_full = bars + 2 * MAX_STAGES;    // [GROUPS] MMA -> softmax: the scores of the group's next block are complete
@@ -305,6 +335,8 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
     tc::tmem_alloc(tmem_ptr_smem, TMEM_COLS);
     tc::tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < ONES_BYTES / 4; i += THREADS) reinterpret_cast<uint32_t*>(ones_smem)[i] = 0x3f803f80u;   // bf16 1.0 pairs
+  tc::fence_proxy_async();   // generic-proxy stores -> visible to the tensor core
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -355,6 +387,8 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
     const int g = warp - MMA_WARP;
     constexpr uint32_t idesc_s = idesc_bf16(TILE, TILE, false);
     constexpr uint32_t idesc_o = idesc_bf16(TILE, HEAD_DIM, true);
+    constexpr uint32_t idesc_l = idesc_bf16(TILE, 16, false);
+    const uint64_t ones_desc = desc_k_sw64(tc::smem_u32(ones_smem));   // 16 "columns" x 16 keys of ones, K-major: rows of 64 bytes
     const uint32_t smem_base = tc::smem_u32(smem);
     const uint32_t p_base0 = tc::smem_u32(p_smem) + (uint32_t)(g * P_BUFS * P_BYTES);
     // (all lanes run the control flow; one elected lane issues)
@@ -369,6 +403,9 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
       const int stage = qk.it % n_stages;
       tc::mbar_wait(&kv_full[stage], (uint32_t)(qk.it / n_stages) & 1);
       tc::mbar_wait(&s_free[g], (n_qk & 1) ^ 1);
+      long long* tr = nullptr;
+      if (TRACE && blockIdx.x == 0 && lane == 0 && n_qk < (uint32_t)TRACE_BLOCKS && g_trace) tr = g_trace + SOFTMAX_WARPS * TRACE_BLOCKS * 8 + ((size_t)g * TRACE_BLOCKS + n_qk) * 4;
+      if (TRACE && tr) tr[2] = clock64();
       tc::tc_fence_after();
       const uint32_t base = smem_base + (uint32_t)stage * (uint32_t)stage_bytes;
       const uint64_t q_desc = desc_k_sw64(base + (uint32_t)(qk.qt * QKV_TILE_BYTES));
@@ -381,6 +418,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
         tc::umma_commit(&s_full[g]);
       }
       __syncwarp();
+      if (TRACE && tr) tr[3] = clock64();
       ++n_qk;
       if (++qk_b == qk.n_tiles) { qk_b = 0; qk_ready = false; }   // the next job is looked up when its turn comes
     };
@@ -388,6 +426,9 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
       const int stage = pv.it % n_stages;
       const int buf = (int)(n_pv % P_BUFS);
       tc::mbar_wait(&p_full[2 * g + buf], (n_pv / P_BUFS) & 1);
+      long long* tr = nullptr;
+      if (TRACE && blockIdx.x == 0 && lane == 0 && n_pv < (uint32_t)TRACE_BLOCKS && g_trace) tr = g_trace + SOFTMAX_WARPS * TRACE_BLOCKS * 8 + ((size_t)g * TRACE_BLOCKS + n_pv) * 4;
+      if (TRACE && tr) tr[0] = clock64();
       tc::tc_fence_after();
       const uint32_t base = smem_base + (uint32_t)stage * (uint32_t)stage_bytes;
       // +16 keys: 32 bytes inside P's 128-byte swizzle row (4 steps per 64-key atom), 1024 bytes down V's rows
@@ -399,12 +440,16 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
       if (tc::elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < TILE / 16; ++kk)
-          tc::umma_bf16(tmem_base + O_COL + g * HEAD_DIM, a_desc + (uint64_t)((kk >> 2) * (P_ATOM_BYTES >> 4) + (kk & 3) * 2),
-                        b_desc + (uint64_t)(kk * (1024 >> 4)), idesc_o, (pv_b | kk) != 0 ? 1u : 0u);
+        {
+          const uint64_t a_kk = a_desc + (uint64_t)((kk >> 2) * (P_ATOM_BYTES >> 4) + (kk & 3) * 2);
+          tc::umma_bf16(tmem_base + O_COL + g * OL_COLS, a_kk, b_desc + (uint64_t)(kk * (1024 >> 4)), idesc_o, (pv_b | kk) != 0 ? 1u : 0u);
+          tc::umma_bf16(tmem_base + O_COL + g * OL_COLS + HEAD_DIM, a_kk, ones_desc, idesc_l, (pv_b | kk) != 0 ? 1u : 0u);
+        }
         tc::umma_commit(&o_full[2 * g + buf]);
         if (release) tc::umma_commit(&kv_empty[stage]);   // every MMA of this group that reads the unit's stage has been issued
       }
       __syncwarp();
+      if (TRACE && tr) tr[1] = clock64();
       ++n_pv;
       if (last_in_job) {
         pv_b = 0;
@@ -443,23 +488,29 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_tmem = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t s_tmem = lane_tmem + (uint32_t)(g * TILE);
-    const uint32_t o_tmem = lane_tmem + (uint32_t)(O_COL + g * HEAD_DIM);
+    const uint32_t o_tmem = lane_tmem + (uint32_t)(O_COL + g * OL_COLS);   // O, then L at +32
     const float lazy_raw = LAZY_LOG2 / scale_log2;
     const uint64_t scale2 = pack_f32x2(scale_log2, scale_log2);
+    (void)add_f32x2;
     uint32_t k = 0;   // key blocks this group has processed (-> barrier phases, P buffer)
     // waits until P V of the group's block n has retired (the MMAs retire in order: so have all earlier ones)
     auto wait_pv = [&](uint32_t n) { tc::mbar_wait(&o_full[2 * g + (int)(n % P_BUFS)], (n / P_BUFS) & 1); };
     Cursor w;
     while (w.template seek<false, true>(g, split, published, desc, no_skip), !w.done) {
-      float m = -INFINITY, l = 0.f;
+      float m = -INFINITY;
       for (int b = 0; b < w.n_tiles; ++b, ++k) {
         const int valid = w.S - b * TILE;            // keys of this block inside the sequence (>= 1)
         uint32_t r[TILE];
+        long long* tr = nullptr;
+        if (TRACE && blockIdx.x == 0 && lane == 0 && k < (uint32_t)TRACE_BLOCKS && g_trace) tr = g_trace + ((size_t)warp * TRACE_BLOCKS + k) * 8;
+        if (TRACE && tr) tr[0] = clock64();
         tc::mbar_wait(&s_full[g], k & 1);
+        if (TRACE && tr) tr[1] = clock64();
         tc::tc_fence_after();
 #pragma unroll
         for (int c = 0; c < TILE / 32; ++c) tc::tmem_ld32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
         tc::tmem_ld_wait();
+        if (TRACE && tr) tr[2] = clock64();
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&s_free[g]);   // the next block's scores may overwrite the buffer
@@ -468,14 +519,20 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
           for (int i = 0; i < TILE; ++i)
             if (i >= valid) r[i] = 0xff800000u;       // keys beyond the sequence
         }
-        float mb = max3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
-        float mb2 = max3(__uint_as_float(r[3]), __uint_as_float(r[4]), __uint_as_float(r[5]));
+        // four independent chains of 3-input maxima
+        float mx[4];
 #pragma unroll
-        for (int i = 6; i + 3 < TILE; i += 4) {
-          mb = max3(mb, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-          mb2 = max3(mb2, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+        for (int c = 0; c < 4; ++c) mx[c] = max3(__uint_as_float(r[3 * c]), __uint_as_float(r[3 * c + 1]), __uint_as_float(r[3 * c + 2]));
+#pragma unroll
+        for (int i = 12; i + 7 < TILE; i += 8) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) mx[c] = max3(mx[c], __uint_as_float(r[i + 2 * c]), __uint_as_float(r[i + 2 * c + 1]));
         }
-        mb = max3(mb, mb2, fmaxf(__uint_as_float(r[TILE - 2]), __uint_as_float(r[TILE - 1])));
+        // 12 + 8 * 14 = 124: four scores left
+        mx[0] = max3(mx[0], __uint_as_float(r[TILE - 4]), __uint_as_float(r[TILE - 3]));
+        mx[1] = max3(mx[1], __uint_as_float(r[TILE - 2]), __uint_as_float(r[TILE - 1]));
+        const float mb = max3(fmaxf(mx[0], mx[1]), mx[2], mx[3]);
+        if (TRACE && tr) tr[3] = clock64() + (long long)(mb == 12345.f);   // (depends on the maximum: stamps after it)
         // the reference: block 0 sets it (key 0 is always valid: finite); later blocks raise it lazily
         float corr = 1.f;
         bool raise = false;
@@ -486,10 +543,9 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
           m = mb;
           raise = true;
         }
-        // p = 2^(s c - m c) on pairs; the row sum from the unrounded weights
+        // p = 2^(s c - m c), truncated to bf16 pairs (the row sums are taken by the tensor core over the same values)
         const float off = m * scale_log2;
         const uint64_t noff2 = pack_f32x2(-off, -off);
-        uint64_t l2a = pack_f32x2(0.f, 0.f), l2b = l2a;
         uint32_t pk[TILE / 2];
 #pragma unroll
         for (int i = 0; i < TILE; i += 4) {
@@ -508,31 +564,28 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
             unpack_f32x2(xb, p2, p3);
             p2 = ex2(p2); p3 = ex2(p3);
           }
-          l2a = add_f32x2(l2a, pack_f32x2(p0, p1));
-          l2b = add_f32x2(l2b, pack_f32x2(p2, p3));
-          pk[i >> 1] = pack2(p0, p1);
-          pk[(i >> 1) + 1] = pack2(p2, p3);
+          pk[i >> 1] = trunc_bf16x2(p0, p1);
+          pk[(i >> 1) + 1] = trunc_bf16x2(p2, p3);
         }
+        if (TRACE && tr) tr[4] = clock64() + (long long)(pk[TILE / 2 - 1] == 0x12345678u);   // (after the last exponential)
         // the P V of P_BUFS blocks ago has retired: its P buffer is reusable
         if (k >= (uint32_t)P_BUFS) wait_pv(k - P_BUFS);
+        if (TRACE && tr) tr[5] = clock64();
         if (b > 0 && __any_sync(0xffffffffu, raise)) {
-          // rare: a raised reference rescales the running O (complete once the previous P V has retired) and l
+          // rare: a raised reference rescales the running O and L (complete once the previous P V has retired)
           if (P_BUFS > 1) wait_pv(k - 1);
           tc::tc_fence_after();
-          uint32_t o[HEAD_DIM];
+          uint32_t o[HEAD_DIM], ls[16];
           tc::tmem_ld32(o_tmem, o);
+          tmem_ld16(o_tmem + HEAD_DIM, ls);
           tc::tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < HEAD_DIM; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ls[i] = __float_as_uint(__uint_as_float(ls[i]) * corr);
           tc::tmem_st32(o_tmem, o);
+          tmem_st16(o_tmem + HEAD_DIM, ls);
           tc::tmem_st_wait();
-          l *= corr;
-        }
-        {
-          float la, lb, lc, ld;
-          unpack_f32x2(l2a, la, lb);
-          unpack_f32x2(l2b, lc, ld);
-          l += (la + lb) + (lc + ld);
         }
         // 16-byte chunk j of row r lives at chunk (j ^ (r & 7)) of the row's 128 bytes
         const uint32_t p_row = tc::smem_u32(p_smem + (size_t)(g * P_BUFS + (int)(k % P_BUFS)) * P_BYTES) + (uint32_t)row * 128u;
@@ -542,18 +595,21 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + (uint32_t)((j >> 3) * P_ATOM_BYTES) + chunk * 16u),
                        "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
         }
+        if (TRACE && tr) tr[6] = clock64();
         tc::fence_proxy_async();   // P (generic-proxy stores) -> visible to the tensor core
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&p_full[2 * g + (int)(k % P_BUFS)]);
+        if (TRACE && tr) tr[7] = clock64();
       }
       // ---------------- end of job: O / l -> ctx ----------------
       wait_pv(k - 1);
       tc::tc_fence_after();
       uint32_t o[HEAD_DIM];
       tc::tmem_ld32(o_tmem, o);
+      const float l = __uint_as_float(tc::tmem_ld1(o_tmem + HEAD_DIM));   // every column of L holds the row sum
       tc::tmem_ld_wait();
-      tc::tc_fence_before();   // ordered before this warp's next p_full arrival (the next job's first P V overwrites O)
+      tc::tc_fence_before();   // ordered before this warp's next p_full arrival (the next job's first P V overwrites O and L)
       const int qrow = w.qt * TILE + row;
       if (qrow < w.S) {
         const float inv = 1.f / l;

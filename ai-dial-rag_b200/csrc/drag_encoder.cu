@@ -434,7 +434,7 @@ int launch_gemm(const drag_encoder* e, const CUtensorMap& ta, const CUtensorMap&
 int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* qkv, bf16* ctx, const int32_t* d_cu,
                      int n_seq, int max_len, int heads, cudaStream_t st) {
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)HEAD_DIM);
-  if (variant >= 3 && variant <= 6) {
+  if (variant >= 3 && variant <= 7) {
     // tcgen05, two out-of-phase softmax groups (drag_attention_tc3.cuh); variant 4 double-buffers P, variants 5 / 6
     // compute 25 % / 50 % of the exponentials on the FMA pipe
     const int p_bufs = variant == 4 ? 2 : 1;
@@ -454,6 +454,8 @@ int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* q
       attn3::attention_tc3_kernel<2, 0><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2);
     else if (variant == 5)
       attn3::attention_tc3_kernel<1, 4><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2);
+    else if (variant == 7)   // phase timeline of CTA 0 (drag_debug_attention_trace)
+      attn3::attention_tc3_kernel<1, 0, true><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2);
     else if (variant == 6)
       attn3::attention_tc3_kernel<1, 2><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2);
     else
@@ -506,6 +508,7 @@ int attention_set_attributes() {
   DRAG_CUDA_OK(cudaFuncSetAttribute(attn3::attention_tc3_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3_max[0]));
   DRAG_CUDA_OK(cudaFuncSetAttribute(attn3::attention_tc3_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3_max[0]));
   DRAG_CUDA_OK(cudaFuncSetAttribute(attn3::attention_tc3_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3_max[1]));
+  DRAG_CUDA_OK(cudaFuncSetAttribute(attn3::attention_tc3_kernel<1, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3_max[0]));
   DRAG_CUDA_OK(cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::smem_bytes(512)));
   DRAG_CUDA_OK(cudaFuncSetAttribute(attn_tc::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_max));
   DRAG_CUDA_OK(cudaFuncSetAttribute(attn_tc2::attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2_max));
@@ -960,7 +963,7 @@ extern "C" int drag_debug_attention(int device, int variant, const void* d_qkv, 
                                     int n_seq, int n_tokens, int max_len, int heads, void* stream) {
   DRAG_REQUIRE(d_qkv && d_ctx && d_cu_seqlens && n_seq >= 1 && heads >= 1 && n_tokens >= 1, "drag_debug_attention: bad arguments");
   DRAG_REQUIRE(max_len >= 1 && max_len <= 512, "drag_debug_attention: max_len must be in 1..512");
-  DRAG_REQUIRE(variant >= 0 && variant <= 6, "drag_debug_attention: variant 0 (mma.sync), 1, 2 (earlier tcgen05 designs), 3..6 (tcgen05, two softmax groups; 4 double-buffers P, 5 / 6 put 25 / 50 %% of the exponentials on the FMA pipe)");
+  DRAG_REQUIRE(variant >= 0 && variant <= 7, "drag_debug_attention: variant 0 (mma.sync), 1, 2 (earlier tcgen05 designs), 3..6 (tcgen05, two softmax groups; 4 double-buffers P, 5 / 6 put 25 / 50 %% of the exponentials on the FMA pipe)");
   DeviceGuard guard(device);
   if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_debug_attention: cannot select device %d", device);
   int rc = attention_set_attributes();
@@ -970,6 +973,18 @@ extern "C" int drag_debug_attention(int device, int variant, const void* d_qkv, 
       (rc = make_tmap_bf16_box(&tm, d_qkv, (uint64_t)n_tokens, (uint64_t)3 * heads * HEAD_DIM, attn_tc::TILE, attn_tc::HEAD_DIM)))
     return rc;
   return launch_attention(variant, tm, (const bf16*)d_qkv, (bf16*)d_ctx, d_cu_seqlens, n_seq, max_len, heads, (cudaStream_t)stream);
+}
+
+// Phase timeline of the tcgen05 attention kernel (debug): points the kernel's trace pointer at `d_trace`
+// (int64[drag_debug_attention_trace_words()], zeroed by the caller; nullptr switches tracing off); variant 7 of
+// drag_debug_attention then records clock64() stamps of CTA 0.
+extern "C" int drag_debug_attention_trace_words(void) { return attn3::TRACE_WORDS; }
+extern "C" int drag_debug_set_attention_trace(int device, void* d_trace) {
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_debug_set_attention_trace: cannot select device %d", device);
+  long long* p = (long long*)d_trace;
+  DRAG_CUDA_OK(cudaMemcpyToSymbol(attn3::g_trace, &p, sizeof(p)));
+  return DRAG_OK;
 }
 
 // ---------------------------------------------------------------------------------

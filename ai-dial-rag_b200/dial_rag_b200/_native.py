@@ -80,6 +80,8 @@ _SIGNATURES = {
     "drag_debug_gemm": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int,
                                   C.c_float, C.c_float, _P]),
     "drag_debug_attention": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "drag_debug_attention_trace_words": (C.c_int, []),
+    "drag_debug_set_attention_trace": (C.c_int, [C.c_int, _P]),
     "drag_wordpiece_create": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_P)]),
     "drag_wordpiece_destroy": (C.c_int, [_P]),
     "drag_wordpiece_encode": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),

@@ -126,6 +126,9 @@ int drag_encoder_forward_debug(drag_encoder* enc, const int32_t* d_ids, const in
  *   {embed+LN, QKV GEMM, attention, out-proj GEMM+LN, FFN-up GEMM+GELU, FFN-down GEMM+LN, pool,
  *    CLS-only tail of the last layer}.  Only forwards in the bulk workspace are recorded.
  */
+/* Debug: phase timeline (clock64 stamps of CTA 0) of the tcgen05 attention kernel, see scripts/attn_trace.py. */
+int drag_debug_attention_trace_words(void);
+int drag_debug_set_attention_trace(int device, void* d_trace);
 int drag_encoder_profile_begin(drag_encoder* enc, int max_launches);
 int drag_encoder_profile_end(drag_encoder* enc, double* ms_by_class, int* launches_by_class);
 
