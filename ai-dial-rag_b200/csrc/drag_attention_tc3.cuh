@@ -1,39 +1,41 @@
 // Multi-head self-attention on tcgen05 for the packed (padding-free) batch, head_dim = 32
 // (SURVEY.md 8a row a5:  softmax(Q K^T / sqrt(32) + key mask) V ).  Third design.
 //
-// At head_dim 32 the op is bound by the exponentials (one per 128 flop; MUFU: 16 per clock per SM, measured),
-// so the kernel is arranged around ONE rule: a softmax warp never waits for anything another softmax warp of
-// the other group could be computing exponentials behind.
+// At head_dim 32 the op is bound by the exponentials (one per 128 flop; MUFU: 16 per clock per SM, measured), so
+// the kernel is built to keep the MUFU pipe fed: everything a softmax warp does besides exponentials was measured
+// with an in-kernel timeline (scripts/attn_trace.py) and removed or shortened.
 //
 // Persistent kernel, one CTA per SM, 11 working warps (12 launched: register budgets are set per warpgroup):
 //   warps 0-3   softmax group 0        thread = one query row of the group's current 128-query job
-//   warps 4-7   softmax group 1        (jobs alternate between the groups: the two run out of phase)
+//   warps 4-7   softmax group 1        (jobs alternate between the groups)
 //   warp  8     TMA producer: Q, K and V tiles (128 tokens x one head, 64-byte swizzle) of the next units
-//               straight out of the packed [T, 3*hidden] QKV buffer into a 1..4-stage ring
-//   warps 9,10  MMA issuers, one per softmax group, so the groups never wait for each other's tiles whatever the
-//               sequence lengths are.  The whole warp walks the job sequence (warp-uniform values: descriptors live
-//               in uniform registers) and one elected lane issues -- a P V step is only 16 clocks of tensor work, so
-//               the cost of ISSUING a tcgen05.mma matters here
-// The producer publishes a small descriptor of every unit next to its ring stage: the issuer and the softmax
-// warps walk the job sequence on shared memory only (a walker on global loads stalled the issuer for
-// thousands of cycles per job).
+//               straight out of the packed [T, 3*hidden] QKV buffer into a 2..4-stage ring
+//   warps 9,10  MMA issuers, one per softmax group.  The whole warp walks the job sequence (warp-uniform values:
+//               descriptors live in uniform registers) and one lane picked by elect.sync issues -- `if (lane == 0)`
+//               makes ptxas wrap every tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA loop, and a P V step is only
+//               16 clocks of tensor work, so the cost of ISSUING matters here.
+// The producer publishes a small descriptor of every unit in shared memory; all walkers run on those.
 // A unit = one (sequence, head) item, or 1/split of its query tiles when few items are in flight (the query
 // path); a job = one 128-query tile of a unit against all keys of the sequence, in 128-key blocks.
-// Per job and key block, in group g:
-//   S[128 x 128] = Q K^T        tcgen05.mma M=128 N=128 K=16 x2 -> TMEM columns [128 g, +128)
-//   softmax thread              ONE tcgen05.ld pass: the row's 128 scores go to registers and the S buffer is
-//                               handed back at once (the next block's scores are computed behind this block's
-//                               exponentials); row maximum, lazily raised reference m (only when a score
-//                               exceeds it by 2^8: the softmax is invariant to the reference), p = 2^(s c - m c)
-//                               (FFMA2 + MUFU.EX2), bf16 pairs by TRUNCATION (one PRMT per pair: the F2FP
-//                               conversion runs at a third of the ALU rate, measured) into the group's P buffer
-//                               (K-major, 128-byte swizzle: the A operand of P V)
-//   O[128 x 32] (+)= P V        tcgen05.mma M=128 N=32 K=16 x8 into TMEM columns [256 + 48 g, +32); V is
-//   L[128 x 16] (+)= P 1        consumed as stored ([key][32]: an MN-major B operand); the row sums come out of the
-//                               tensor core over exactly the truncated weights of the numerator (the truncation
-//                               bias cancels in O / L, and the softmax loop carries no additions).  O and L stay
-//                               in TMEM across the key blocks of a job; a raised reference rescales them (rare).
-//   end of job                  O / L -> bf16 -> ctx (rows inside the sequence only)
+//
+// TMEM (256 columns per group):  S [0,128)  scores of the next block | P [128,192)  bf16 weights, two per column |
+//                                O [192,224) and [224,256)  output accumulators of the group's even / odd jobs
+// Per key block n of group g:
+//   S(n) = Q K^T               tcgen05.mma M=128 N=128 K=16 x2, issued as soon as S(n-1) is in registers
+//   softmax thread             ONE tcgen05.ld pass (128 scores -> registers, S handed back at once); row maximum
+//                              (8 chains of 3-input maxima), lazily raised reference m (only when a score exceeds it by
+//                              2^8: the softmax is invariant to the reference), p = 2^(s c - m c) (FFMA2 + MUFU.EX2),
+//                              row sum in registers, bf16 pairs by add-half-ulp + PRMT (the F2FP conversion runs at a
+//                              third of the ALU rate, measured); then one barrier wait -- inside a job for S(n+1), whose
+//                              completion also says that P(n-1) V has retired (same issuing thread, issued earlier), at
+//                              a job's last block for P(n-1) V itself: the P columns are free and O is complete up to
+//                              block n-1 -- and P goes to TMEM with two tcgen05.st (no shared-memory round trip, no
+//                              proxy fence)
+//   O (+)= P(n) V              tcgen05.mma M=128 N=32 K=16 x8 with A FROM TMEM; V is consumed as stored ([key][32]:
+//                              an MN-major B operand).  O stays in TMEM across the key blocks of a job; a raised
+//                              reference rescales it in place (rare).
+//   end of job                 O / l -> bf16 -> ctx (rows inside the sequence only), DEFERRED into the next block's
+//                              barrier wait (the accumulators alternate between jobs), so nobody waits for a P V
 // Keys beyond the sequence do not exist in the packed layout: the tail of the last block is masked before the
 // row maximum.  Every row's result depends on that row's scores only (no cross-row decision), so it does not
 // depend on the batch composition.
@@ -53,28 +55,27 @@ constexpr int GROUPS = 2;
 constexpr int SOFTMAX_WARPS = 4 * GROUPS;
 constexpr int TMA_WARP = SOFTMAX_WARPS;
 constexpr int MMA_WARP = TMA_WARP + 1;                  // issuer of group 0; MMA_WARP + 1: group 1
-constexpr int THREADS = 384;                            // 3 warpgroups: softmax 0, softmax 1, {TMA, MMA, two idle warps}
+constexpr int THREADS = 384;                            // 3 warpgroups: softmax 0, softmax 1, {TMA, 2 x MMA, one idle warp}
 constexpr int SOFTMAX_REGS = 200;                       // setmaxnreg: 8 x 32 x 200 + 4 x 32 x 104 = 64 512 = 384 x 168
 constexpr int OTHER_REGS = 104;
 constexpr int TMEM_COLS = 512;
-constexpr int O_COL = GROUPS * TILE;                    // group g: S at [128 g, +128), O at [256 + 48 g, +32), L at [256 + 48 g + 32, +16)
-constexpr int OL_COLS = HEAD_DIM + 16;                  // O and the row sums L = P . 1 (a 16-column MMA against a tile of ones)
-constexpr int ONES_BYTES = 1024;                        // [16][32] bf16 ones (all equal: layout and swizzle do not matter)
-constexpr int P_ATOM_BYTES = TILE * 64 * 2;             // 16 KB: [128 rows][64 keys] bf16, 128-byte swizzle
-constexpr int P_BYTES = 2 * P_ATOM_BYTES;               // one 128-key block of P
+constexpr int GROUP_COLS = 256;                         // per group: S [0,128) | P [128,192) | O even jobs [192,224) | O odd jobs [224,256)
+constexpr int P_COL = TILE;
+constexpr int O_COL = TILE + TILE / 2;
 constexpr int MAX_STAGES = 4;
 constexpr int SMEM_BUDGET = 227 * 1024;
 constexpr int BAR_BYTES = 512;
 constexpr float LAZY_LOG2 = 8.f;                        // numerators stay <= 2^8
 
-__host__ __device__ inline int unit_stages(int max_len, int p_bufs) {
+// ring stages (no P buffers in shared memory any more: even 512-token units get two)
+__host__ __device__ inline int unit_stages(int max_len) {
   const int tiles = (max_len + TILE - 1) / TILE;
-  const int fit = (SMEM_BUDGET - GROUPS * p_bufs * P_BYTES - ONES_BYTES - 1024 - BAR_BYTES) / (3 * tiles * QKV_TILE_BYTES);
-  return fit < 1 ? 1 : (fit < MAX_STAGES ? fit : MAX_STAGES);
+  const int fit = (SMEM_BUDGET - 1024 - BAR_BYTES) / (3 * tiles * QKV_TILE_BYTES);
+  return fit < MAX_STAGES ? fit : MAX_STAGES;   // 4, 4, 3, 2 stages for 1..4 tiles
 }
-__host__ __device__ inline size_t smem_bytes(int max_len, int p_bufs) {
+__host__ __device__ inline size_t smem_bytes(int max_len) {
   const int tiles = (max_len + TILE - 1) / TILE;
-  return (size_t)unit_stages(max_len, p_bufs) * 3 * tiles * QKV_TILE_BYTES + (size_t)GROUPS * p_bufs * P_BYTES + ONES_BYTES + 1024 /*alignment*/ + BAR_BYTES;
+  return (size_t)unit_stages(max_len) * 3 * tiles * QKV_TILE_BYTES + 1024 /*alignment*/ + BAR_BYTES;
 }
 // few items in flight (the query path): an item's query tiles are dealt to `split` units so that the launch fills the GPU
 __host__ __device__ inline int pick_split(int n_items, int max_len, int sms) {
@@ -109,6 +110,15 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, bool b_mn_major)
   return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(m >> 4) << 24);
 }
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (bf16 pairs, one 32-bit column per two k) comes from tensor memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -142,29 +152,11 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
-// 2^x for a pair on the FMA / ALU pipes instead of the MUFU pipe (16 ex2 per clock per SM is what bounds this kernel):
-// x = j + f with j = round(x) (magic-number add), 2^f for f in [-0.5, 0.5] by a degree-3 polynomial (relative error 1.0e-4,
-// a twentieth of the bf16 rounding the weight gets next), then j goes straight into the exponent field.  Valid for
-// x in [-126, 127): smaller arguments are clamped (2^-126 is as good as 0 for a softmax weight).
-__device__ __forceinline__ void exp2_poly_pair(uint64_t x2, float& p0, float& p1) {
-  float x0, x1;
-  unpack_f32x2(x2, x0, x1);
-  x0 = fmaxf(x0, -126.f);
-  x1 = fmaxf(x1, -126.f);
-  const uint64_t xc = pack_f32x2(x0, x1);
-  const uint64_t t2 = add_f32x2(xc, pack_f32x2(12582912.f, 12582912.f));          // 1.5 * 2^23: j in the low mantissa bits
-  const uint64_t j2 = add_f32x2(t2, pack_f32x2(-12582912.f, -12582912.f));
-  const uint64_t f2 = fma_f32x2(j2, pack_f32x2(-1.f, -1.f), xc);
-  uint64_t q2 = fma_f32x2(f2, pack_f32x2(0.05500893f, 0.05500893f), pack_f32x2(0.24221095f, 0.24221095f));
-  q2 = fma_f32x2(q2, f2, pack_f32x2(0.6932829f, 0.6932829f));
-  q2 = fma_f32x2(q2, f2, pack_f32x2(1.f, 1.f));
-  float t0, t1, q0, q1;
-  unpack_f32x2(t2, t0, t1);
-  unpack_f32x2(q2, q0, q1);
-  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
-  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+// two non-negative fp32 -> bf16 pair, rounded half up: add half an ulp to the bits, keep the high halves (2 IADD + 1 PRMT
+// on the ALU pipe instead of one F2FP at a third of its rate)
+__device__ __forceinline__ uint32_t round_bf16x2(float lo, float hi) {
+  return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
 }
-
 // non-blocking probe (try_wait may suspend the thread)
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -177,24 +169,14 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
+__device__ __forceinline__ int ld_acquire_shared(const int* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared::cta.b32 %0, [%1];" : "=r"(v) : "r"(tc::smem_u32(p)) : "memory");
+  return v;
 }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15};"
-      ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(taddr)
-      : "memory");
+__device__ __forceinline__ void st_release_shared(int* p, int v) {
+  asm volatile("st.release.cta.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(p)), "r"(v) : "memory");
 }
-// two non-negative fp32 -> bf16 pair by truncation (high halves): one PRMT
-__device__ __forceinline__ uint32_t trunc_bf16x2(float lo, float hi) { return __byte_perm(__float_as_uint(lo), __float_as_uint(hi), 0x7632); }
 
 // What the TMA producer publishes about every unit, in a ring of DESC_RING descriptors indexed by the unit's ordinal,
 // BEFORE it waits for the unit's data; `published` counts them.  S = 0 marks the end of the CTA's stream.
@@ -208,20 +190,10 @@ struct UnitDesc {
   int head;
   int part;        // first query tile of the unit (then part + split, ...)
 };
+constexpr int DESC_RING = 2 * MAX_STAGES;
 
 // The CTA's jobs in a fixed order: its units in ring order, per unit the query tiles part, part + split, ...; job ordinal
 // n (CTA-wide) belongs to softmax group n & 1.  A cursor points at one job of one group.
-constexpr int DESC_RING = 2 * MAX_STAGES;
-
-__device__ __forceinline__ int ld_acquire_shared(const int* p) {
-  int v;
-  asm volatile("ld.acquire.cta.shared::cta.b32 %0, [%1];" : "=r"(v) : "r"(tc::smem_u32(p)) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_shared(int* p, int v) {
-  asm volatile("st.release.cta.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(p)), "r"(v) : "memory");
-}
-
 struct Cursor {
   int it = 0;        // ordinal of the unit (-> ring stage it % n_stages, phase it / n_stages; descriptor it % DESC_RING)
   int job = -1;      // CTA-wide job ordinal of the current job
@@ -271,40 +243,36 @@ struct Cursor {
   __device__ __forceinline__ bool last_of_group_in_unit(int split) const { return qt + 2 * split >= n_tiles; }
 };
 
-// qkv : [T, 3*hidden] bf16 (tensor map: box 32 columns x 128 rows, 64-byte swizzle)
-// ctx : [T, hidden] bf16
-// grid = min(#SMs, units), block = THREADS, dynamic smem = smem_bytes(longest sequence, P_BUFS)
 // Debug timeline (TRACE instantiation only, scripts/attn_trace.py): CTA 0 records clock64() at the phase boundaries of its
 // first TRACE_BLOCKS key blocks -- per softmax warp 8 stamps per block, per issuer 4 stamps per block.
 constexpr int TRACE_BLOCKS = 96;
 constexpr int TRACE_WORDS = SOFTMAX_WARPS * TRACE_BLOCKS * 8 + GROUPS * TRACE_BLOCKS * 4;
 __device__ long long* g_trace = nullptr;
 
-// POLY: every POLY-th pair of weights is computed by exp2_poly_pair instead of MUFU.EX2 (0 = none, 4 = 25 %, 2 = 50 %)
-template <int P_BUFS, int POLY, bool TRACE = false>
+// qkv : [T, 3*hidden] bf16 (tensor map: box 32 columns x 128 rows, 64-byte swizzle)
+// ctx : [T, hidden] bf16
+// grid = min(#SMs, units), block = THREADS, dynamic smem = smem_bytes(longest sequence)
+template <bool TRACE = false>
 __global__ void __launch_bounds__(THREADS, 1)
 attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ ctx,
                      const int* __restrict__ cu_seqlens, int n_seq, int heads, int max_tiles, int n_stages, int split,
-                     float scale_log2) {
+                     float scale_log2, int stagger) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int hidden = heads * HEAD_DIM;
   const size_t stage_bytes = (size_t)3 * max_tiles * QKV_TILE_BYTES;  // [Q tiles | K tiles | V tiles]
-  uint8_t* p_smem = smem + (size_t)n_stages * stage_bytes;            // multiple of 8 KB: 1024-aligned
-  uint8_t* ones_smem = p_smem + (size_t)GROUPS * P_BUFS * P_BYTES;   // 1024-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ones_smem + ONES_BYTES);
-  uint64_t* kv_full = bars;                    // [MAX_STAGES] TMA -> everybody: the unit (and its descriptor) has landed
-  uint64_t* kv_empty = bars + MAX_STAGES;      // [MAX_STAGES] MMA -> TMA (every MMA that reads the unit has retired)
-  uint64_t* s_full = bars + 2 * MAX_STAGES;    // [GROUPS] MMA -> softmax: the scores of the group's next block are complete
-  uint64_t* s_free = s_full + GROUPS;          // [GROUPS] softmax -> MMA: the scores are in registers
-  uint64_t* p_full = s_free + GROUPS;          // [GROUPS][2] softmax -> MMA: P of the group's block n is in shared memory (and O is
-                                               //             rescaled): barrier n % P_BUFS, phase n / P_BUFS
-  uint64_t* o_full = p_full + 2 * GROUPS;      // [GROUPS][2] MMA -> softmax: P V of block n has retired (P buffer n % P_BUFS reusable,
-                                               //             O complete up to block n): barrier n % P_BUFS, phase n / P_BUFS
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 2 * GROUPS);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)n_stages * stage_bytes);
+  uint64_t* kv_full = bars;                    // [MAX_STAGES] TMA -> MMA: the unit has landed
+  uint64_t* kv_empty = bars + MAX_STAGES;      // [MAX_STAGES] MMA -> TMA: one arrival per issuer (after its last P V in the unit, or on passing it)
+  uint64_t* s_full = bars + 2 * MAX_STAGES;    // [GROUPS] MMA -> softmax: phase n = the scores of the group's block n are complete
+                                               //          (and so is every MMA the group's issuer had issued before them)
+  uint64_t* s_free = s_full + GROUPS;          // [GROUPS] softmax -> MMA: phase n = the scores of block n are in registers
+  uint64_t* p_full = s_free + GROUPS;          // [GROUPS] softmax -> MMA: phase n = P(n) is in tensor memory (and O is rescaled / read out)
+  uint64_t* o_full = p_full + GROUPS;          // [GROUPS] MMA -> softmax: phase n = P(n) V has retired (waited for at the end of the stream only)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + GROUPS);
   int* published = reinterpret_cast<int*>(tmem_ptr_smem + 1);        // descriptors written so far
   UnitDesc* desc = reinterpret_cast<UnitDesc*>(tmem_ptr_smem + 2);   // [DESC_RING]
-  static_assert((2 * MAX_STAGES + 6 * GROUPS) * 8 + 8 + DESC_RING * sizeof(UnitDesc) <= BAR_BYTES, "barrier region too small");
+  static_assert((2 * MAX_STAGES + 4 * GROUPS) * 8 + 8 + DESC_RING * sizeof(UnitDesc) <= BAR_BYTES, "barrier region too small");
   auto no_skip = [](int) {};
 
   const int warp = threadIdx.x >> 5;
@@ -316,15 +284,13 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
       tc::tma_prefetch_desc(&tmap_qkv);
       for (int s = 0; s < MAX_STAGES; ++s) {
         tc::mbar_init(&kv_full[s], 1);
-        tc::mbar_init(&kv_empty[s], GROUPS);   // one arrival per issuer: after its last P V in the unit, or on passing a unit without a job of its group
+        tc::mbar_init(&kv_empty[s], GROUPS);
       }
       for (int g = 0; g < GROUPS; ++g) {
         tc::mbar_init(&s_full[g], 1);
         tc::mbar_init(&s_free[g], 4);
-        for (int b = 0; b < 2; ++b) {
-          tc::mbar_init(&p_full[2 * g + b], 4);
-          tc::mbar_init(&o_full[2 * g + b], 1);
-        }
+        tc::mbar_init(&p_full[g], 4);
+        tc::mbar_init(&o_full[g], 1);
       }
       *published = 0;
       tc::fence_barrier_init();
@@ -335,8 +301,6 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
     tc::tmem_alloc(tmem_ptr_smem, TMEM_COLS);
     tc::tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < ONES_BYTES / 4; i += THREADS) reinterpret_cast<uint32_t*>(ones_smem)[i] = 0x3f803f80u;   // bf16 1.0 pairs
-  tc::fence_proxy_async();   // generic-proxy stores -> visible to the tensor core
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -382,23 +346,22 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
    } else if (warp == MMA_WARP || warp == MMA_WARP + 1) {
     // ===================== MMA issuer of group g:  S(0) | { S(n+1), P(n) V } ... =====================
     // Per group the events alternate strictly -- s_free(n) (the scores of block n are in registers) precedes p_full(n) --
-    // so blocking waits in that order never stall the other group, which has its own issuer.  The next block's scores
-    // are issued BEFORE P(n) V unless their unit has not landed yet (its ring stage may be waiting for this very P V).
+    // so blocking waits in that order never stall the other group, which has its own issuer.  INSIDE a job S(n+1) is
+    // always issued before P(n) V and after P(n-1) V: the softmax threads rely on that order (s_full(n+1) tells them that
+    // P(n-1) V is done).  Across jobs the next job's first scores go out early only if its unit has landed already -- with
+    // a full ring it may be waiting for this very P V -- and the softmax threads wait for P(n-1) V itself.
     const int g = warp - MMA_WARP;
     constexpr uint32_t idesc_s = idesc_bf16(TILE, TILE, false);
     constexpr uint32_t idesc_o = idesc_bf16(TILE, HEAD_DIM, true);
-    constexpr uint32_t idesc_l = idesc_bf16(TILE, 16, false);
-    const uint64_t ones_desc = desc_k_sw64(tc::smem_u32(ones_smem));   // 16 "columns" x 16 keys of ones, K-major: rows of 64 bytes
     const uint32_t smem_base = tc::smem_u32(smem);
-    const uint32_t p_base0 = tc::smem_u32(p_smem) + (uint32_t)(g * P_BUFS * P_BYTES);
-    // (all lanes run the control flow; one elected lane issues)
+    const uint32_t tmem_g = tmem_base + (uint32_t)(g * GROUP_COLS);
     Cursor qk, pv;
     int qk_b = 0, pv_b = 0;
-    uint32_t n_qk = 0, n_pv = 0;
+    uint32_t n_qk = 0, n_pv = 0, pv_job = 0;
     bool qk_ready = false;   // qk points at a block whose scores have not been issued yet
+    auto landed = [&](int it) { return __all_sync(0xffffffffu, mbar_test(&kv_full[it % n_stages], (uint32_t)(it / n_stages) & 1)); };
     // a unit passed without a job of this group: its ring stage does not wait for this issuer
     auto skip_unit = [&](int it) { if (lane == 0) tc::mbar_arrive(&kv_empty[it % n_stages]); };
-    auto landed = [&](int it) { return __all_sync(0xffffffffu, mbar_test(&kv_full[it % n_stages], (uint32_t)(it / n_stages) & 1)); };
     auto issue_scores = [&]() {
       const int stage = qk.it % n_stages;
       tc::mbar_wait(&kv_full[stage], (uint32_t)(qk.it / n_stages) & 1);
@@ -414,7 +377,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
       if (tc::elect_one()) {
 #pragma unroll
         for (int k = 0; k < HEAD_DIM / 16; ++k)
-          tc::umma_bf16(tmem_base + g * TILE, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc_s, k != 0 ? 1u : 0u);
+          tc::umma_bf16(tmem_g, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc_s, k != 0 ? 1u : 0u);
         tc::umma_commit(&s_full[g]);
       }
       __syncwarp();
@@ -424,28 +387,37 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
     };
     auto issue_pv = [&]() {
       const int stage = pv.it % n_stages;
-      const int buf = (int)(n_pv % P_BUFS);
-      tc::mbar_wait(&p_full[2 * g + buf], (n_pv / P_BUFS) & 1);
+      tc::mbar_wait(&p_full[g], n_pv & 1);
       long long* tr = nullptr;
       if (TRACE && blockIdx.x == 0 && lane == 0 && n_pv < (uint32_t)TRACE_BLOCKS && g_trace) tr = g_trace + SOFTMAX_WARPS * TRACE_BLOCKS * 8 + ((size_t)g * TRACE_BLOCKS + n_pv) * 4;
       if (TRACE && tr) tr[0] = clock64();
       tc::tc_fence_after();
       const uint32_t base = smem_base + (uint32_t)stage * (uint32_t)stage_bytes;
-      // +16 keys: 32 bytes inside P's 128-byte swizzle row (4 steps per 64-key atom), 1024 bytes down V's rows
-      const uint64_t a_desc = tc::umma_desc_sw128(p_base0 + (uint32_t)(buf * P_BYTES));
+      // +16 keys: 8 columns of P (two bf16 per column), 1024 bytes down V's rows
       const uint64_t b_desc = desc_mn_sw64(base + (uint32_t)((2 * max_tiles + pv_b) * QKV_TILE_BYTES));
+      const uint32_t o_tmem = tmem_g + (uint32_t)(O_COL + (pv_job & 1) * HEAD_DIM);
       const bool last_in_job = pv_b + 1 == pv.n_tiles;
       const bool release = last_in_job && pv.last_of_group_in_unit(split);
+      // Keys beyond the sequence: their weights are exact zeros, but the V rows behind them belong to other sequences or
+      // to the never-written tail of the buffer and may hold anything, NaN included (0 x NaN = NaN).  Only the 16-key steps
+      // that contain a key of the sequence are issued, and the rows of the last step beyond the sequence are zeroed in
+      // shared memory first (both groups' issuers may do that for the same tile: same zeros).
+      const int valid = pv.S - pv_b * TILE;
+      const int n_steps = valid >= TILE ? TILE / 16 : (valid + 15) >> 4;
+      if (valid < n_steps * 16) {
+        const uint32_t v_tile = base + (uint32_t)((2 * max_tiles + pv_b) * QKV_TILE_BYTES);
+        const int chunks = (n_steps * 16 - valid) * 4;   // 16-byte chunks (the 64-byte swizzle permutes chunks inside a row only)
+        for (int c = lane; c < chunks; c += 32)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(v_tile + (uint32_t)(valid * 64 + c * 16)), "r"(0u) : "memory");
+        tc::fence_proxy_async();
+      }
       __syncwarp();
       if (tc::elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < TILE / 16; ++kk)
-        {
-          const uint64_t a_kk = a_desc + (uint64_t)((kk >> 2) * (P_ATOM_BYTES >> 4) + (kk & 3) * 2);
-          tc::umma_bf16(tmem_base + O_COL + g * OL_COLS, a_kk, b_desc + (uint64_t)(kk * (1024 >> 4)), idesc_o, (pv_b | kk) != 0 ? 1u : 0u);
-          tc::umma_bf16(tmem_base + O_COL + g * OL_COLS + HEAD_DIM, a_kk, ones_desc, idesc_l, (pv_b | kk) != 0 ? 1u : 0u);
-        }
-        tc::umma_commit(&o_full[2 * g + buf]);
+          if (kk < n_steps)
+            umma_bf16_ts(o_tmem, tmem_g + (uint32_t)(P_COL + kk * 8), b_desc + (uint64_t)(kk * (1024 >> 4)), idesc_o, (pv_b | kk) != 0 ? 1u : 0u);
+        tc::umma_commit(&o_full[g]);
         if (release) tc::umma_commit(&kv_empty[stage]);   // every MMA of this group that reads the unit's stage has been issued
       }
       __syncwarp();
@@ -453,6 +425,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
       ++n_pv;
       if (last_in_job) {
         pv_b = 0;
+        ++pv_job;
         // Blocking is safe here: everything this group owes the current unit has been issued, so the unit's stage
         // (which the next descriptor may be waiting for) is released by the other group's issuer alone.
         pv.template seek<true, true>(g, split, published, desc, skip_unit);
@@ -465,13 +438,18 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
     qk_ready = !qk.done;
     if (qk_ready) issue_scores();
     while (!pv.done) {
-      // the scores of the next block go out BEFORE P(n) V -- unless their unit (or even its descriptor) is not there yet:
-      // with a full ring it is waiting for this very P V
-      if (!qk_ready && !qk.done) qk_ready = qk.template seek<true, false>(g, split, published, desc, no_skip) && !qk.done;
       bool scored = false;
-      if (qk_ready && landed(qk.it)) {
+      if (qk_ready) {
+        // inside a job: the next block's scores first, always (same unit: landed)
         issue_scores();
         scored = true;
+      } else if (!qk.done) {
+        // the next job's first scores: early only if its descriptor is published and its unit has landed
+        qk_ready = qk.template seek<true, false>(g, split, published, desc, no_skip) && !qk.done;
+        if (qk_ready && landed(qk.it)) {
+          issue_scores();
+          scored = true;
+        }
       }
       issue_pv();
       if (!scored && !qk.done) {
@@ -486,27 +464,55 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SOFTMAX_REGS));
     const int g = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
-    const uint32_t lane_tmem = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t s_tmem = lane_tmem + (uint32_t)(g * TILE);
-    const uint32_t o_tmem = lane_tmem + (uint32_t)(O_COL + g * OL_COLS);   // O, then L at +32
+    const uint32_t lane_tmem = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * GROUP_COLS);
+    const uint32_t s_tmem = lane_tmem;
+    const uint32_t p_tmem = lane_tmem + P_COL;
     const float lazy_raw = LAZY_LOG2 / scale_log2;
     const uint64_t scale2 = pack_f32x2(scale_log2, scale_log2);
-    (void)add_f32x2;
-    uint32_t k = 0;   // key blocks this group has processed (-> barrier phases, P buffer)
-    // waits until P V of the group's block n has retired (the MMAs retire in order: so have all earlier ones)
-    auto wait_pv = [&](uint32_t n) { tc::mbar_wait(&o_full[2 * g + (int)(n % P_BUFS)], (n / P_BUFS) & 1); };
+    uint32_t k = 0;      // key blocks this group has processed (-> barrier phases)
+    uint32_t jobs = 0;   // jobs this group has finished (-> O accumulator parity)
+    // a finished job whose output is still in its accumulator
+    bool pend = false;
+    float pend_l = 1.f;
+    int pend_row = 0, pend_tok0 = 0, pend_head = 0, pend_acc = 0;
+    bool pend_valid = false;
+    auto flush = [&]() {   // O / l -> ctx of the pending job; its last P V has retired (the caller has seen to that)
+      uint32_t o[HEAD_DIM];
+      tc::tmem_ld32(lane_tmem + (uint32_t)(O_COL + pend_acc * HEAD_DIM), o);
+      tc::tmem_ld_wait();
+      if (pend_valid) {
+        const float inv = 1.f / pend_l;
+        uint4* dst = reinterpret_cast<uint4*>(ctx + (size_t)(pend_tok0 + pend_row) * hidden + pend_head * HEAD_DIM);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          dst[j] = make_uint4(pack2(__uint_as_float(o[8 * j]) * inv, __uint_as_float(o[8 * j + 1]) * inv),
+                              pack2(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv),
+                              pack2(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv),
+                              pack2(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv));
+      }
+      pend = false;
+    };
+    // The two groups do identical work: started together they stay in phase and meet at the MUFU pipe, each at half its
+    // rate, while the pipe idles during their (equally simultaneous) loads, maxima and waits.  Group 1 starts `stagger`
+    // clocks late; nothing pulls the groups back into phase, so the offset persists.
+    if (g == 1 && stagger > 0) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < (long long)stagger) {}
+    }
     Cursor w;
     while (w.template seek<false, true>(g, split, published, desc, no_skip), !w.done) {
-      float m = -INFINITY;
+      float m = -INFINITY, l = 0.f;
       for (int b = 0; b < w.n_tiles; ++b, ++k) {
         const int valid = w.S - b * TILE;            // keys of this block inside the sequence (>= 1)
         uint32_t r[TILE];
         long long* tr = nullptr;
         if (TRACE && blockIdx.x == 0 && lane == 0 && k < (uint32_t)TRACE_BLOCKS && g_trace) tr = g_trace + ((size_t)warp * TRACE_BLOCKS + k) * 8;
         if (TRACE && tr) tr[0] = clock64();
-        tc::mbar_wait(&s_full[g], k & 1);
+        if (b == 0) {   // (the scores of a job's later blocks were waited for one block ahead)
+          tc::mbar_wait(&s_full[g], k & 1);
+          tc::tc_fence_after();
+        }
         if (TRACE && tr) tr[1] = clock64();
-        tc::tc_fence_after();
 #pragma unroll
         for (int c = 0; c < TILE / 32; ++c) tc::tmem_ld32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
         tc::tmem_ld_wait();
@@ -519,19 +525,19 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
           for (int i = 0; i < TILE; ++i)
             if (i >= valid) r[i] = 0xff800000u;       // keys beyond the sequence
         }
-        // four independent chains of 3-input maxima
-        float mx[4];
+        // eight independent chains of 3-input maxima
+        float mx[8];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) mx[c] = max3(__uint_as_float(r[3 * c]), __uint_as_float(r[3 * c + 1]), __uint_as_float(r[3 * c + 2]));
+        for (int c = 0; c < 8; ++c) mx[c] = max3(__uint_as_float(r[3 * c]), __uint_as_float(r[3 * c + 1]), __uint_as_float(r[3 * c + 2]));
 #pragma unroll
-        for (int i = 12; i + 7 < TILE; i += 8) {
+        for (int i = 24; i + 15 < TILE; i += 16) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) mx[c] = max3(mx[c], __uint_as_float(r[i + 2 * c]), __uint_as_float(r[i + 2 * c + 1]));
+          for (int c = 0; c < 8; ++c) mx[c] = max3(mx[c], __uint_as_float(r[i + 2 * c]), __uint_as_float(r[i + 2 * c + 1]));
         }
-        // 12 + 8 * 14 = 124: four scores left
-        mx[0] = max3(mx[0], __uint_as_float(r[TILE - 4]), __uint_as_float(r[TILE - 3]));
-        mx[1] = max3(mx[1], __uint_as_float(r[TILE - 2]), __uint_as_float(r[TILE - 1]));
-        const float mb = max3(fmaxf(mx[0], mx[1]), mx[2], mx[3]);
+        // 24 + 16 * 6 = 120: eight scores left
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mx[c] = max3(mx[c], __uint_as_float(r[120 + 2 * c]), __uint_as_float(r[121 + 2 * c]));
+        const float mb = max3(max3(mx[0], mx[1], mx[2]), max3(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7]));
         if (TRACE && tr) tr[3] = clock64() + (long long)(mb == 12345.f);   // (depends on the maximum: stamps after it)
         // the reference: block 0 sets it (key 0 is always valid: finite); later blocks raise it lazily
         float corr = 1.f;
@@ -543,84 +549,71 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
           m = mb;
           raise = true;
         }
-        // p = 2^(s c - m c), truncated to bf16 pairs (the row sums are taken by the tensor core over the same values)
+        // p = 2^(s c - m c); row sum from the unrounded weights; bf16 pairs (two per P column)
         const float off = m * scale_log2;
         const uint64_t noff2 = pack_f32x2(-off, -off);
+        uint64_t l2a = pack_f32x2(0.f, 0.f), l2b = l2a;
         uint32_t pk[TILE / 2];
 #pragma unroll
         for (int i = 0; i < TILE; i += 4) {
           float p0, p1, p2, p3;
-          const uint64_t xa = fma_f32x2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), scale2, noff2);
-          const uint64_t xb = fma_f32x2(pack_f32x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), scale2, noff2);
-          if (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == 0) {
-            exp2_poly_pair(xa, p0, p1);
-          } else {
-            unpack_f32x2(xa, p0, p1);
-            p0 = ex2(p0); p1 = ex2(p1);
-          }
-          if (POLY > 0 && (((i >> 1) + 1) % (POLY > 0 ? POLY : 1)) == 0) {
-            exp2_poly_pair(xb, p2, p3);
-          } else {
-            unpack_f32x2(xb, p2, p3);
-            p2 = ex2(p2); p3 = ex2(p3);
-          }
-          pk[i >> 1] = trunc_bf16x2(p0, p1);
-          pk[(i >> 1) + 1] = trunc_bf16x2(p2, p3);
+          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), scale2, noff2), p0, p1);
+          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), scale2, noff2), p2, p3);
+          p0 = ex2(p0); p1 = ex2(p1); p2 = ex2(p2); p3 = ex2(p3);
+          l2a = add_f32x2(l2a, pack_f32x2(p0, p1));
+          l2b = add_f32x2(l2b, pack_f32x2(p2, p3));
+          pk[i >> 1] = round_bf16x2(p0, p1);
+          pk[(i >> 1) + 1] = round_bf16x2(p2, p3);
         }
         if (TRACE && tr) tr[4] = clock64() + (long long)(pk[TILE / 2 - 1] == 0x12345678u);   // (after the last exponential)
-        // the P V of P_BUFS blocks ago has retired: its P buffer is reusable
-        if (k >= (uint32_t)P_BUFS) wait_pv(k - P_BUFS);
+        // One wait before P is stored.  Inside a job: the next block's scores S(k+1) -- issued after P(k-1) V by the same
+        // thread, so P(k-1) V has retired as well.  At a job's last block: P(k-1) V itself.  Either way the P columns are
+        // free and O is complete up to block k-1.
+        if (b + 1 < w.n_tiles) tc::mbar_wait(&s_full[g], (k + 1) & 1);
+        else if (k > 0) tc::mbar_wait(&o_full[g], (k - 1) & 1);
+        tc::tc_fence_after();
         if (TRACE && tr) tr[5] = clock64();
+        if (pend) flush();   // the previous job's output (its accumulator is the other one)
         if (b > 0 && __any_sync(0xffffffffu, raise)) {
-          // rare: a raised reference rescales the running O and L (complete once the previous P V has retired)
-          if (P_BUFS > 1) wait_pv(k - 1);
-          tc::tc_fence_after();
-          uint32_t o[HEAD_DIM], ls[16];
+          // rare: a raised reference rescales the running O (complete: P(k-1) V has retired) and l
+          const uint32_t o_tmem = lane_tmem + (uint32_t)(O_COL + (jobs & 1) * HEAD_DIM);
+          uint32_t o[HEAD_DIM];
           tc::tmem_ld32(o_tmem, o);
-          tmem_ld16(o_tmem + HEAD_DIM, ls);
           tc::tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < HEAD_DIM; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) ls[i] = __float_as_uint(__uint_as_float(ls[i]) * corr);
           tc::tmem_st32(o_tmem, o);
-          tmem_st16(o_tmem + HEAD_DIM, ls);
-          tc::tmem_st_wait();
+          l *= corr;
         }
-        // 16-byte chunk j of row r lives at chunk (j ^ (r & 7)) of the row's 128 bytes
-        const uint32_t p_row = tc::smem_u32(p_smem + (size_t)(g * P_BUFS + (int)(k % P_BUFS)) * P_BYTES) + (uint32_t)row * 128u;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const uint32_t chunk = (uint32_t)((j & 7) ^ (row & 7));
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + (uint32_t)((j >> 3) * P_ATOM_BYTES) + chunk * 16u),
-                       "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
+        {
+          float la, lb, lc, ld;
+          unpack_f32x2(l2a, la, lb);
+          unpack_f32x2(l2b, lc, ld);
+          l += (la + lb) + (lc + ld);
         }
+        tc::tmem_st32(p_tmem, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+        tc::tmem_st32(p_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
+        tc::tmem_st_wait();
         if (TRACE && tr) tr[6] = clock64();
-        tc::fence_proxy_async();   // P (generic-proxy stores) -> visible to the tensor core
         tc::tc_fence_before();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&p_full[2 * g + (int)(k % P_BUFS)]);
+        if (lane == 0) tc::mbar_arrive(&p_full[g]);
         if (TRACE && tr) tr[7] = clock64();
       }
-      // ---------------- end of job: O / l -> ctx ----------------
-      wait_pv(k - 1);
+      // the job's output stays in its accumulator until the next block's wait (or the end of the stream)
+      pend = true;
+      pend_l = l;
+      pend_row = w.qt * TILE + row;
+      pend_valid = pend_row < w.S;
+      pend_tok0 = w.tok0;
+      pend_head = w.head;
+      pend_acc = (int)(jobs & 1);
+      ++jobs;
+    }
+    if (pend) {
+      tc::mbar_wait(&o_full[g], (k - 1) & 1);
       tc::tc_fence_after();
-      uint32_t o[HEAD_DIM];
-      tc::tmem_ld32(o_tmem, o);
-      const float l = __uint_as_float(tc::tmem_ld1(o_tmem + HEAD_DIM));   // every column of L holds the row sum
-      tc::tmem_ld_wait();
-      tc::tc_fence_before();   // ordered before this warp's next p_full arrival (the next job's first P V overwrites O and L)
-      const int qrow = w.qt * TILE + row;
-      if (qrow < w.S) {
-        const float inv = 1.f / l;
-        uint4* dst = reinterpret_cast<uint4*>(ctx + (size_t)(w.tok0 + qrow) * hidden + w.head * HEAD_DIM);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          dst[j] = make_uint4(pack2(__uint_as_float(o[8 * j]) * inv, __uint_as_float(o[8 * j + 1]) * inv),
-                              pack2(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv),
-                              pack2(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv),
-                              pack2(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv));
-      }
+      flush();
     }
   }
 

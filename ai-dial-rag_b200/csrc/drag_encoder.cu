@@ -434,10 +434,8 @@ int launch_gemm(const drag_encoder* e, const CUtensorMap& ta, const CUtensorMap&
 int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* qkv, bf16* ctx, const int32_t* d_cu,
                      int n_seq, int max_len, int heads, cudaStream_t st) {
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)HEAD_DIM);
-  if (variant >= 3 && variant <= 7) {
-    // tcgen05, two out-of-phase softmax groups (drag_attention_tc3.cuh); variant 4 double-buffers P, variants 5 / 6
-    // compute 25 % / 50 % of the exponentials on the FMA pipe
-    const int p_bufs = variant == 4 ? 2 : 1;
+  if (variant == 3 || variant == 7) {
+    // tcgen05, two softmax groups, P in tensor memory (drag_attention_tc3.cuh); variant 7 = the same with the debug timeline
     int sms = 148;
     {
       int dev = 0;
@@ -446,20 +444,15 @@ int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* q
     const int items = heads * n_seq;
     const int split = attn3::pick_split(items, max_len, sms);
     const int units = items * split;
-    const size_t smem = attn3::smem_bytes(max_len, p_bufs);
+    const size_t smem = attn3::smem_bytes(max_len);
     const int max_tiles = (max_len + attn3::TILE - 1) / attn3::TILE;
     const int grid = units < sms ? units : sms;
-    const int stages = attn3::unit_stages(max_len, p_bufs);
-    if (variant == 4)
-      attn3::attention_tc3_kernel<2, 0><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2);
-    else if (variant == 5)
-      attn3::attention_tc3_kernel<1, 4><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2);
-    else if (variant == 7)   // phase timeline of CTA 0 (drag_debug_attention_trace)
-      attn3::attention_tc3_kernel<1, 0, true><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2);
-    else if (variant == 6)
-      attn3::attention_tc3_kernel<1, 2><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2);
+    const int stages = attn3::unit_stages(max_len);
+    static const int stagger = [] { const char* v = getenv("DRAG_ATTN_STAGGER"); return v ? atoi(v) : 0; }();   // clocks group 1 starts late
+    if (variant == 7)
+      attn3::attention_tc3_kernel<true><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2, stagger);
     else
-      attn3::attention_tc3_kernel<1, 0><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2);
+      attn3::attention_tc3_kernel<false><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2, stagger);
   } else if (variant == 2) {
     const size_t smem = attn_tc2::smem_bytes(max_len);
     const int items = heads * n_seq;
@@ -497,18 +490,14 @@ int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* q
 
 int attention_set_attributes() {
   // the shared-memory need is not monotonic in the sequence length (fewer stages for longer items): take the maximum
-  size_t tc_max = 0, tc2_max = 0, tc3_max[2] = {0, 0};
+  size_t tc_max = 0, tc2_max = 0, tc3_max = 0;
   for (int len = 128; len <= 512; len += 128) {
     tc_max = attn_tc::smem_bytes(len) > tc_max ? attn_tc::smem_bytes(len) : tc_max;
     tc2_max = attn_tc2::smem_bytes(len) > tc2_max ? attn_tc2::smem_bytes(len) : tc2_max;
-    for (int pb = 1; pb <= 2; ++pb)
-      tc3_max[pb - 1] = attn3::smem_bytes(len, pb) > tc3_max[pb - 1] ? attn3::smem_bytes(len, pb) : tc3_max[pb - 1];
+    tc3_max = attn3::smem_bytes(len) > tc3_max ? attn3::smem_bytes(len) : tc3_max;
   }
-  DRAG_CUDA_OK(cudaFuncSetAttribute(attn3::attention_tc3_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3_max[0]));
-  DRAG_CUDA_OK(cudaFuncSetAttribute(attn3::attention_tc3_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3_max[0]));
-  DRAG_CUDA_OK(cudaFuncSetAttribute(attn3::attention_tc3_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3_max[0]));
-  DRAG_CUDA_OK(cudaFuncSetAttribute(attn3::attention_tc3_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3_max[1]));
-  DRAG_CUDA_OK(cudaFuncSetAttribute(attn3::attention_tc3_kernel<1, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3_max[0]));
+  DRAG_CUDA_OK(cudaFuncSetAttribute(attn3::attention_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3_max));
+  DRAG_CUDA_OK(cudaFuncSetAttribute(attn3::attention_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3_max));
   DRAG_CUDA_OK(cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::smem_bytes(512)));
   DRAG_CUDA_OK(cudaFuncSetAttribute(attn_tc::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_max));
   DRAG_CUDA_OK(cudaFuncSetAttribute(attn_tc2::attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2_max));
@@ -812,9 +801,6 @@ extern "C" int drag_encoder_create(const drag_bert_shape* shape, const float* co
     if (v && strcmp(v, "tc") == 0) e->attention_variant = 1;
     if (v && strcmp(v, "tc2") == 0) e->attention_variant = 2;
     if (v && strcmp(v, "tc3") == 0) e->attention_variant = 3;
-    if (v && strcmp(v, "tc3p2") == 0) e->attention_variant = 4;
-    if (v && strcmp(v, "tc3e25") == 0) e->attention_variant = 5;
-    if (v && strcmp(v, "tc3e50") == 0) e->attention_variant = 6;
     const char* gm = getenv("DRAG_GEMM_PAIRS");
     if (gm && gm[0] >= '0' && gm[0] <= '9') e->gemm_pairs = atoi(gm) & 31;
     const char* co = getenv("DRAG_CLS_ONLY");
@@ -963,7 +949,7 @@ extern "C" int drag_debug_attention(int device, int variant, const void* d_qkv, 
                                     int n_seq, int n_tokens, int max_len, int heads, void* stream) {
   DRAG_REQUIRE(d_qkv && d_ctx && d_cu_seqlens && n_seq >= 1 && heads >= 1 && n_tokens >= 1, "drag_debug_attention: bad arguments");
   DRAG_REQUIRE(max_len >= 1 && max_len <= 512, "drag_debug_attention: max_len must be in 1..512");
-  DRAG_REQUIRE(variant >= 0 && variant <= 7, "drag_debug_attention: variant 0 (mma.sync), 1, 2 (earlier tcgen05 designs), 3..6 (tcgen05, two softmax groups; 4 double-buffers P, 5 / 6 put 25 / 50 %% of the exponentials on the FMA pipe)");
+  DRAG_REQUIRE(variant == 0 || variant == 1 || variant == 2 || variant == 3 || variant == 7, "drag_debug_attention: variant 0 (mma.sync), 1, 2 (earlier tcgen05 designs), 3 (tcgen05, two softmax groups, P in tensor memory), 7 (3 with the debug timeline)");
   DeviceGuard guard(device);
   if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_debug_attention: cannot select device %d", device);
   int rc = attention_set_attributes();

@@ -37,7 +37,7 @@ t = trace.cpu().numpy()
 NB = 96
 soft = t[: 8 * NB * 8].reshape(8, NB, 8)
 iss = t[8 * NB * 8:].reshape(2, NB, 4)
-names = ["wait s_full", "ld S (4 x tcgen05.ld)", "row max", "exponentials", "wait o_full", "store P", "fence + arrive", "-> next block top"]
+names = ["wait s_full (job start only)", "ld S (4 x tcgen05.ld)", "row max", "exponentials", "wait S(next) / PV(prev)", "flush + rescale + st P", "fence + arrive", "-> next block top"]
 print(f"{a.seqs} x {a.len}: cycles per phase of a key block (median over blocks 8..{NB - 8}), CTA 0")
 for w in range(8):
     s = soft[w]

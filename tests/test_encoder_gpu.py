@@ -96,7 +96,7 @@ def test_tcgen05_gemm_vs_torch(variant, N, K, M):
 
 @pytest.mark.parametrize("lens", [[1, 2, 17, 64, 65, 128, 256, 300, 512, 33], [512], [300, 77], [130] * 4],
                          ids=["ragged10", "one512", "two", "four130"])
-@pytest.mark.parametrize("variant", [6, 5, 4, 3, 2, 1, 0])
+@pytest.mark.parametrize("variant", [3, 2, 1, 0])
 def test_attention_vs_torch(variant, lens):
     """Every attention kernel against torch fp32 softmax(QK^T/sqrt(32))V per packed sequence; the short
     batches exercise the 128- and 64-query tiles the mma.sync kernel picks when few sequences are in flight."""
@@ -121,6 +121,50 @@ def test_attention_vs_torch(variant, lens):
         ref = (p @ v).permute(1, 0, 2).reshape(n, heads * hd)
         err = (got[cu[i]:cu[i + 1]] - ref).abs().max().item()
         assert err <= 0.03, (variant, n, err)
+
+
+@pytest.mark.parametrize("variant", [3, 0])
+def test_attention_peaked_garbage_tail_and_batch_invariance(variant):
+    """What the encoder does to an attention kernel and random inputs do not: peaked logits (the reference of a row is
+    raised between key blocks), NaN in the never-written rows behind the last sequence (0 x NaN must not reach anybody's
+    output), and bit-identical rows whether a sequence is processed alone or inside a batch."""
+    native, lib = _lib()
+    heads, hd = 12, 32
+    lens = [5, 130, 101, 2, 257, 64, 400]
+    cu = np.zeros(len(lens) + 1, dtype=np.int32)
+    cu[1:] = np.cumsum(lens)
+    T = int(cu[-1])
+    tail = 200
+    g = torch.Generator(device="cuda").manual_seed(9)
+    qkv = torch.randn(T + tail, 3 * heads * hd, device="cuda", generator=g) * 1.5
+    qkv[:, : 2 * heads * hd] *= 3.0                       # logits of +-100 before the 1/sqrt(32): sharply peaked rows
+    qkv = _bf16(qkv)
+    qkv[T:] = float("nan")
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run(q, cu_np, n_tokens):
+        ctx = torch.full((n_tokens, heads * hd), float("nan"), device="cuda", dtype=torch.bfloat16)
+        d_cu = torch.from_numpy(cu_np).cuda()
+        lens_ = np.diff(cu_np)
+        native.check(lib.drag_debug_attention(0, variant, q.data_ptr(), ctx.data_ptr(), d_cu.data_ptr(), len(lens_), n_tokens,
+                                              int(lens_.max()), heads, st))
+        torch.cuda.synchronize()
+        return ctx
+
+    whole = run(qkv, cu, T + tail)
+    got = whole[:T].float()
+    assert torch.isfinite(got).all()
+    for i, n in enumerate(lens):
+        blk = qkv[cu[i]:cu[i + 1]].float().view(n, 3, heads, hd)
+        q, k, v = (blk[:, j].permute(1, 0, 2) for j in range(3))
+        p = torch.softmax(q @ k.transpose(1, 2) / math.sqrt(hd), dim=-1)
+        ref = (p @ v).permute(1, 0, 2).reshape(n, heads * hd)
+        err = (got[cu[i]:cu[i + 1]] - ref).abs().max().item()
+        assert err <= 0.06, (variant, n, err)
+        # the same sequence alone, again followed by NaN rows
+        alone = torch.cat((qkv[cu[i]:cu[i + 1]], qkv[T:T + 130]))
+        one = run(alone, np.array([0, n], dtype=np.int32), n + 130)
+        assert torch.equal(one[:n], whole[cu[i]:cu[i + 1]]), (variant, n)
 
 
 @pytest.fixture(scope="module", params=["hf_init", "stress", "outlier"])

@@ -209,6 +209,7 @@ def test_config1_alps_wiki_corpus(tmp_path):
     tok = WordPieceTokenizer.from_vocab_file(build_vocab_file(str(tmp_path), texts + ALPS_QUERIES))
     w = oenc.synth_weights(seed=0, style="hf_init")
     impl = emb.B200BgeEmbeddings(w, tok, device=0, max_tokens=65536)
+    previous = emb._impl          # (the module-scoped `stack` fixture of the other tests in this file)
     emb.configure(impl)
     try:
         chunks = [Chunk(text=t, metadata={"chunk_id": i}) for i, t in enumerate(texts)]
@@ -234,7 +235,7 @@ def test_config1_alps_wiki_corpus(tmp_path):
             assert got[0][1] == best_orc[1] or abs(d_best - d_got) <= 4e-3, (q, got[0], best_orc)
         assert retriever.batch(ALPS_QUERIES) == [retriever.invoke(q) for q in ALPS_QUERIES]
     finally:
-        emb.configure(None)
+        emb.configure(previous)
         impl.client.close()
 
 
