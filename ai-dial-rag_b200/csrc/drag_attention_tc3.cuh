@@ -178,6 +178,80 @@ __device__ __forceinline__ void st_release_shared(int* p, int v) {
   asm volatile("st.release.cta.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(p)), "r"(v) : "memory");
 }
 
+// ---- the softmax of one 128-key block of one row, scores in registers ----
+// PARTIAL (the last block of a sequence whose length is not a multiple of 128): only the 32-key chunks that contain a
+// key of the sequence are loaded / reduced / exponentiated (the rest of P is zero), keys beyond the sequence are masked.
+template <bool PARTIAL>
+__device__ __forceinline__ void load_scores(uint32_t s_tmem, int valid, uint32_t (&r)[TILE]) {
+#pragma unroll
+  for (int c = 0; c < TILE / 32; ++c)
+    if (!PARTIAL || c * 32 < valid) tc::tmem_ld32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
+  tc::tmem_ld_wait();
+}
+template <bool PARTIAL>
+__device__ __forceinline__ float row_max(uint32_t (&r)[TILE], int valid) {
+  if (!PARTIAL) {
+    // eight independent chains of 3-input maxima
+    float mx[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) mx[c] = max3(__uint_as_float(r[3 * c]), __uint_as_float(r[3 * c + 1]), __uint_as_float(r[3 * c + 2]));
+#pragma unroll
+    for (int i = 24; i + 15 < TILE; i += 16) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) mx[c] = max3(mx[c], __uint_as_float(r[i + 2 * c]), __uint_as_float(r[i + 2 * c + 1]));
+    }
+    // 24 + 16 * 6 = 120: eight scores left
+#pragma unroll
+    for (int c = 0; c < 4; ++c) mx[c] = max3(mx[c], __uint_as_float(r[120 + 2 * c]), __uint_as_float(r[121 + 2 * c]));
+    return max3(max3(mx[0], mx[1], mx[2]), max3(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7]));
+  }
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+  for (int c = 0; c < TILE / 32; ++c) {
+    if (c * 32 < valid) {
+      if (valid < (c + 1) * 32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i >= valid) r[c * 32 + i] = 0xff800000u;   // keys beyond the sequence
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mx[j] = max3(mx[j], __uint_as_float(r[c * 32 + i + 2 * j]), __uint_as_float(r[c * 32 + i + 2 * j + 1]));
+      }
+    }
+  }
+  return max3(fmaxf(mx[0], mx[1]), mx[2], mx[3]);
+}
+// p = 2^(s c - m c) as bf16 pairs (two per P column); returns the row sum of the unrounded weights
+template <bool PARTIAL>
+__device__ __forceinline__ float exp_scores(const uint32_t (&r)[TILE], int valid, uint64_t scale2, uint64_t noff2, uint32_t (&pk)[TILE / 2]) {
+  uint64_t l2a = pack_f32x2(0.f, 0.f), l2b = l2a;
+#pragma unroll
+  for (int c = 0; c < TILE / 32; ++c) {
+    if (!PARTIAL || c * 32 < valid) {
+#pragma unroll
+      for (int i = c * 32; i < c * 32 + 32; i += 4) {
+        float p0, p1, p2, p3;
+        unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), scale2, noff2), p0, p1);
+        unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), scale2, noff2), p2, p3);
+        p0 = ex2(p0); p1 = ex2(p1); p2 = ex2(p2); p3 = ex2(p3);
+        l2a = add_f32x2(l2a, pack_f32x2(p0, p1));
+        l2b = add_f32x2(l2b, pack_f32x2(p2, p3));
+        pk[i >> 1] = round_bf16x2(p0, p1);
+        pk[(i >> 1) + 1] = round_bf16x2(p2, p3);
+      }
+    } else {
+#pragma unroll
+      for (int i = c * 16; i < c * 16 + 16; ++i) pk[i] = 0u;
+    }
+  }
+  float la, lb, lc, ld;
+  unpack_f32x2(l2a, la, lb);
+  unpack_f32x2(l2b, lc, ld);
+  return (la + lb) + (lc + ld);
+}
+
 // What the TMA producer publishes about every unit, in a ring of DESC_RING descriptors indexed by the unit's ordinal,
 // BEFORE it waits for the unit's data; `published` counts them.  S = 0 marks the end of the CTA's stream.
 // Jobs alternate between the groups, so a group's cursor passes over at most one unit without a job of its own before
@@ -513,31 +587,18 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
           tc::tc_fence_after();
         }
         if (TRACE && tr) tr[1] = clock64();
-#pragma unroll
-        for (int c = 0; c < TILE / 32; ++c) tc::tmem_ld32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
-        tc::tmem_ld_wait();
+        const bool partial = valid < TILE;   // (the same for every row of the tile)
+        load_scores<false>(s_tmem, valid, r);
         if (TRACE && tr) tr[2] = clock64();
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&s_free[g]);   // the next block's scores may overwrite the buffer
-        if (valid < TILE) {
+        if (partial) {
 #pragma unroll
           for (int i = 0; i < TILE; ++i)
             if (i >= valid) r[i] = 0xff800000u;       // keys beyond the sequence
         }
-        // eight independent chains of 3-input maxima
-        float mx[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) mx[c] = max3(__uint_as_float(r[3 * c]), __uint_as_float(r[3 * c + 1]), __uint_as_float(r[3 * c + 2]));
-#pragma unroll
-        for (int i = 24; i + 15 < TILE; i += 16) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) mx[c] = max3(mx[c], __uint_as_float(r[i + 2 * c]), __uint_as_float(r[i + 2 * c + 1]));
-        }
-        // 24 + 16 * 6 = 120: eight scores left
-#pragma unroll
-        for (int c = 0; c < 4; ++c) mx[c] = max3(mx[c], __uint_as_float(r[120 + 2 * c]), __uint_as_float(r[121 + 2 * c]));
-        const float mb = max3(max3(mx[0], mx[1], mx[2]), max3(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7]));
+        const float mb = row_max<false>(r, valid);
         if (TRACE && tr) tr[3] = clock64() + (long long)(mb == 12345.f);   // (depends on the maximum: stamps after it)
         // the reference: block 0 sets it (key 0 is always valid: finite); later blocks raise it lazily
         float corr = 1.f;
@@ -549,22 +610,11 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
           m = mb;
           raise = true;
         }
-        // p = 2^(s c - m c); row sum from the unrounded weights; bf16 pairs (two per P column)
         const float off = m * scale_log2;
         const uint64_t noff2 = pack_f32x2(-off, -off);
-        uint64_t l2a = pack_f32x2(0.f, 0.f), l2b = l2a;
         uint32_t pk[TILE / 2];
-#pragma unroll
-        for (int i = 0; i < TILE; i += 4) {
-          float p0, p1, p2, p3;
-          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), scale2, noff2), p0, p1);
-          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), scale2, noff2), p2, p3);
-          p0 = ex2(p0); p1 = ex2(p1); p2 = ex2(p2); p3 = ex2(p3);
-          l2a = add_f32x2(l2a, pack_f32x2(p0, p1));
-          l2b = add_f32x2(l2b, pack_f32x2(p2, p3));
-          pk[i >> 1] = round_bf16x2(p0, p1);
-          pk[(i >> 1) + 1] = round_bf16x2(p2, p3);
-        }
+        // (a partial block skips the exponentials of the 32-key chunks that hold no key of the sequence)
+        const float lsum = exp_scores<true>(r, valid, scale2, noff2, pk);
         if (TRACE && tr) tr[4] = clock64() + (long long)(pk[TILE / 2 - 1] == 0x12345678u);   // (after the last exponential)
         // One wait before P is stored.  Inside a job: the next block's scores S(k+1) -- issued after P(k-1) V by the same
         // thread, so P(k-1) V has retired as well.  At a job's last block: P(k-1) V itself.  Either way the P columns are
@@ -585,12 +635,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
           tc::tmem_st32(o_tmem, o);
           l *= corr;
         }
-        {
-          float la, lb, lc, ld;
-          unpack_f32x2(l2a, la, lb);
-          unpack_f32x2(l2b, lc, ld);
-          l += (la + lb) + (lc + ld);
-        }
+        l += lsum;
         tc::tmem_st32(p_tmem, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
         tc::tmem_st32(p_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
         tc::tmem_st_wait();

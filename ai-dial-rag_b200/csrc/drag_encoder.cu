@@ -19,8 +19,6 @@
 #include <vector>
 
 #include "drag_attention.cuh"
-#include "drag_attention_tc.cuh"
-#include "drag_attention_tc2.cuh"
 #include "drag_attention_tc3.cuh"
 #include "drag_common.cuh"
 #include "drag_gemm.cuh"
@@ -453,26 +451,6 @@ int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* q
       attn3::attention_tc3_kernel<true><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2, stagger);
     else
       attn3::attention_tc3_kernel<false><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2, stagger);
-  } else if (variant == 2) {
-    const size_t smem = attn_tc2::smem_bytes(max_len);
-    const int items = heads * n_seq;
-    int sms = 148;
-    {
-      int dev = 0;
-      if (cudaGetDevice(&dev) == cudaSuccess && sm_count(dev) > 0) sms = sm_count(dev);
-    }
-    attn_tc2::attention_tc2_kernel<<<items < sms ? items : sms, attn_tc2::THREADS, smem, st>>>(
-        tm_qkv_heads, ctx, d_cu, n_seq, heads, (max_len + attn_tc::TILE - 1) / attn_tc::TILE, attn_tc2::item_stages(max_len), scale_log2);
-  } else if (variant == 1) {
-    const size_t smem = attn_tc::smem_bytes(max_len);
-    const int items = heads * n_seq;
-    int sms = 148;
-    {
-      int dev = 0;
-      if (cudaGetDevice(&dev) == cudaSuccess && sm_count(dev) > 0) sms = sm_count(dev);
-    }
-    attn_tc::attention_tc_kernel<<<items < sms ? items : sms, attn_tc::THREADS, smem, st>>>(
-        tm_qkv_heads, ctx, d_cu, n_seq, heads, (max_len + attn_tc::TILE - 1) / attn_tc::TILE, attn_tc::item_stages(max_len), scale_log2);
   } else {
     const size_t smem = attn::smem_bytes(max_len);
     // few sequences (the query path): smaller query tiles so that the launch still fills the GPU
@@ -490,17 +468,11 @@ int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* q
 
 int attention_set_attributes() {
   // the shared-memory need is not monotonic in the sequence length (fewer stages for longer items): take the maximum
-  size_t tc_max = 0, tc2_max = 0, tc3_max = 0;
-  for (int len = 128; len <= 512; len += 128) {
-    tc_max = attn_tc::smem_bytes(len) > tc_max ? attn_tc::smem_bytes(len) : tc_max;
-    tc2_max = attn_tc2::smem_bytes(len) > tc2_max ? attn_tc2::smem_bytes(len) : tc2_max;
-    tc3_max = attn3::smem_bytes(len) > tc3_max ? attn3::smem_bytes(len) : tc3_max;
-  }
+  size_t tc3_max = 0;
+  for (int len = 128; len <= 512; len += 128) tc3_max = attn3::smem_bytes(len) > tc3_max ? attn3::smem_bytes(len) : tc3_max;
   DRAG_CUDA_OK(cudaFuncSetAttribute(attn3::attention_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3_max));
   DRAG_CUDA_OK(cudaFuncSetAttribute(attn3::attention_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3_max));
   DRAG_CUDA_OK(cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::smem_bytes(512)));
-  DRAG_CUDA_OK(cudaFuncSetAttribute(attn_tc::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_max));
-  DRAG_CUDA_OK(cudaFuncSetAttribute(attn_tc2::attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2_max));
   return DRAG_OK;
 }
 
@@ -798,9 +770,8 @@ extern "C" int drag_encoder_create(const drag_bert_shape* shape, const float* co
   if ((rc = init_workspace(e, e->ws[1], e->max_tokens < QUERY_WORKSPACE_TOKENS ? e->max_tokens : QUERY_WORKSPACE_TOKENS, true))) return bail(rc);
   {
     const char* v = getenv("DRAG_ATTENTION");
-    if (v && strcmp(v, "tc") == 0) e->attention_variant = 1;
-    if (v && strcmp(v, "tc2") == 0) e->attention_variant = 2;
     if (v && strcmp(v, "tc3") == 0) e->attention_variant = 3;
+    if (v && strcmp(v, "mma") == 0) e->attention_variant = 0;
     const char* gm = getenv("DRAG_GEMM_PAIRS");
     if (gm && gm[0] >= '0' && gm[0] <= '9') e->gemm_pairs = atoi(gm) & 31;
     const char* co = getenv("DRAG_CLS_ONLY");
@@ -949,14 +920,14 @@ extern "C" int drag_debug_attention(int device, int variant, const void* d_qkv, 
                                     int n_seq, int n_tokens, int max_len, int heads, void* stream) {
   DRAG_REQUIRE(d_qkv && d_ctx && d_cu_seqlens && n_seq >= 1 && heads >= 1 && n_tokens >= 1, "drag_debug_attention: bad arguments");
   DRAG_REQUIRE(max_len >= 1 && max_len <= 512, "drag_debug_attention: max_len must be in 1..512");
-  DRAG_REQUIRE(variant == 0 || variant == 1 || variant == 2 || variant == 3 || variant == 7, "drag_debug_attention: variant 0 (mma.sync), 1, 2 (earlier tcgen05 designs), 3 (tcgen05, two softmax groups, P in tensor memory), 7 (3 with the debug timeline)");
+  DRAG_REQUIRE(variant == 0 || variant == 3 || variant == 7, "drag_debug_attention: variant 0 (mma.sync), 3 (tcgen05, two softmax groups, P in tensor memory), 7 (3 with the debug timeline)");
   DeviceGuard guard(device);
   if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_debug_attention: cannot select device %d", device);
   int rc = attention_set_attributes();
   if (rc) return rc;
   CUtensorMap tm;
   if (variant >= 1 &&
-      (rc = make_tmap_bf16_box(&tm, d_qkv, (uint64_t)n_tokens, (uint64_t)3 * heads * HEAD_DIM, attn_tc::TILE, attn_tc::HEAD_DIM)))
+      (rc = make_tmap_bf16_box(&tm, d_qkv, (uint64_t)n_tokens, (uint64_t)3 * heads * HEAD_DIM, attn3::TILE, attn3::HEAD_DIM)))
     return rc;
   return launch_attention(variant, tm, (const bf16*)d_qkv, (bf16*)d_ctx, d_cu_seqlens, n_seq, max_len, heads, (cudaStream_t)stream);
 }

@@ -356,6 +356,41 @@ def bench_query_path(torch, device, weights, rows: int = 1_000_000, q_len: int =
             "queries_per_s_host_api": batch / (host_ms[len(host_ms) // 2] / 1e3),
             "iterations": iters,
         }
+    # ---- batch-1 query latency while an indexing thread keeps the bulk workspace busy (the reference's two
+    # embedding pools, cpu_pools.py:50-59): the query runs in the encoder's query workspace on its high-priority stream
+    import threading
+
+    load_ids = rng.integers(1000, 30522, size=(256, 256), dtype=np.int32)
+    load_ids[:, 0], load_ids[:, -1] = 101, 102
+    load_cu = np.arange(0, 256 * 256 + 1, 256, dtype=np.int32)
+    stop = threading.Event()
+    forwards = [0]
+
+    def indexing_load():
+        while not stop.is_set():
+            enc.embed_packed(load_ids.reshape(-1), load_cu)
+            forwards[0] += 1
+
+    q_ids = rng.integers(1000, 30522, size=(8, q_len), dtype=np.int32)
+    q_ids[:, 0], q_ids[:, -1] = 101, 102
+    q_cu = np.array([0, q_len], dtype=np.int32)
+    worker = threading.Thread(target=indexing_load, daemon=True)
+    worker.start()
+    time.sleep(0.2)
+    lat = []
+    for i in range(300):
+        t0 = time.perf_counter()
+        emb = enc.embed_packed(q_ids[i % 8], q_cu)
+        dm.topk(emb.astype(np.float64), k, "sqeuclidean_dist")
+        lat.append(1e3 * (time.perf_counter() - t0))
+    stop.set()
+    worker.join(timeout=30)
+    lat.sort()
+    out["batch1_under_indexing_load"] = {
+        "host_api_ms_p50": lat[len(lat) // 2], "host_api_ms_p90": lat[int(len(lat) * 0.9)], "host_api_ms_p99": lat[int(len(lat) * 0.99)],
+        "indexing_forwards_during_measurement": forwards[0],
+        "load": "a second host thread embeds 256 x 256-token chunks back to back through the same encoder (bulk workspace)",
+    }
     enc.close()
     del dm, mat, enc
     torch.cuda.empty_cache()
@@ -863,6 +898,8 @@ def main() -> None:
             line["extra"]["query_path"] = qp
             line["e2e"]["query_batch1_host_api_ms_p50"] = qp["batch1"]["host_api_ms_p50"]
             line["e2e"]["query_batch256_qps_host_api"] = qp["batch256"]["queries_per_s_host_api"]
+            line["e2e"]["query_batch1_host_api_ms_p50_under_indexing_load"] = qp["batch1_under_indexing_load"]["host_api_ms_p50"]
+            line["e2e"]["query_batch1_host_api_ms_p99_under_indexing_load"] = qp["batch1_under_indexing_load"]["host_api_ms_p99"]
             roofline["query_batch1_device_ms_p50"] = qp["batch1"]["device_ms_p50"]
             roofline["query_batch256_qps_device"] = qp["batch256"]["queries_per_s_device"]
             line["extra"]["text_path"] = bench_text_path(torch, device, weights)

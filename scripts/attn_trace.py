@@ -62,6 +62,10 @@ for gidx in range(2):
     period = np.median(np.diff(s[idx, 0]))
     print(f"issuer {gidx}: P V issue {int(pv_issue)} cycles, S issue {int(qk_issue)}, p_full -> next p_full {int(period)}; "
           f"after P V issued: s_free wait ends +{int(np.median(s[idx[1:], 2] - s[idx[:-1], 1]))}")
+# phase offset between the groups: start of the exponentials of warp 4 (group 1) relative to warp 0 (group 0), same block ordinal
+idx = np.arange(8, NB - 8)
+off = soft[4][idx, 3] - soft[0][idx, 3]
+print("group 1 starts its exponentials", int(np.median(off)), "cycles after group 0 (median; min", int(off.min()), "max", int(off.max()), ")")
 # cross-role latencies for group 0, warp 0: p_full arrival -> P V issued; s_free arrival -> S issued
 w0 = soft[0]
 for gidx in range(1):

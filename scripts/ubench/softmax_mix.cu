@@ -49,6 +49,66 @@ __global__ void __launch_bounds__(1024) op_kernel(uint32_t* out, long long* cycl
   if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// the loop kernels use NON-volatile forms (the compiler may schedule them like it does in the attention kernel)
+__device__ __forceinline__ uint64_t fma2n(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint64_t add2n(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float ex2n(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float max3n(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+__device__ __forceinline__ uint32_t round_bf16x2(float lo, float hi) { return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632); }
+
+// the attention kernel's loop body as shipped: 8 max chains, fma2 -> ex2 -> add2 (row sum) -> add-half-ulp + PRMT
+// MODE 0: all of it; 1: without the row-sum additions; 2: without the packing; 3: exponentials only (fma2 + ex2)
+template <int MODE>
+__global__ void __launch_bounds__(512) loop2_kernel(uint32_t* out, long long* cycles, uint32_t seed, int blocks) {
+  float r[128];
+#pragma unroll
+  for (int i = 0; i < 128; ++i) r[i] = -0.01f * (float)((threadIdx.x * 7 + i * 13 + seed) & 1023);
+  const uint64_t scale2 = pack2f(0.255f, 0.255f);
+  uint32_t acc = 0;
+  float l = 0.f;
+  __syncthreads();
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (int b = 0; b < blocks; ++b) {
+    float mx[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) mx[c] = max3n(r[3 * c], r[3 * c + 1], r[3 * c + 2]);
+#pragma unroll
+    for (int i = 24; i + 15 < 128; i += 16)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) mx[c] = max3n(mx[c], r[i + 2 * c], r[i + 2 * c + 1]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) mx[c] = max3n(mx[c], r[120 + 2 * c], r[121 + 2 * c]);
+    const float mb = max3n(max3n(mx[0], mx[1], mx[2]), max3n(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7]));
+    const float off = mb * 0.255f;
+    const uint64_t noff2 = pack2f(-off, -off);
+    uint64_t l2a = pack2f(0.f, 0.f), l2b = l2a;
+    uint32_t pk[64];
+    float keep = 0.f;
+#pragma unroll
+    for (int i = 0; i < 128; i += 4) {
+      float p0, p1, p2, p3;
+      unpack2f(fma2n(pack2f(r[i], r[i + 1]), scale2, noff2), p0, p1);
+      unpack2f(fma2n(pack2f(r[i + 2], r[i + 3]), scale2, noff2), p2, p3);
+      p0 = ex2n(p0); p1 = ex2n(p1); p2 = ex2n(p2); p3 = ex2n(p3);
+      if (MODE == 0 || MODE == 2) { l2a = add2n(l2a, pack2f(p0, p1)); l2b = add2n(l2b, pack2f(p2, p3)); }
+      if (MODE == 0 || MODE == 1) { pk[i >> 1] = round_bf16x2(p0, p1); pk[(i >> 1) + 1] = round_bf16x2(p2, p3); }
+      else { pk[i >> 1] = __float_as_uint(p0) ^ __float_as_uint(p1); pk[(i >> 1) + 1] = __float_as_uint(p2) ^ __float_as_uint(p3); }
+    }
+    float la, lb, lc, ld;
+    unpack2f(l2a, la, lb);
+    unpack2f(l2b, lc, ld);
+    l += (la + lb) + (lc + ld) + keep;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc ^= pk[i];
+#pragma unroll
+    for (int i = 0; i < 128; i += 16) r[i] += __uint_as_float((acc & 0x7fu) | 0x3a000000u) * 1e-3f;
+  }
+  const long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc ^ __float_as_uint(l);
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
 __device__ __forceinline__ void exp2_poly_pair(uint64_t x2, float& p0, float& p1) {
   float x0, x1;
   unpack2f(x2, x0, x1);
@@ -154,6 +214,18 @@ int main() {
            (double)threads * 64 * 128 / c, c / 64);                                                             \
   }
   RUN_LOOP(0) RUN_LOOP(4) RUN_LOOP(2)
+  const char* modes[] = {"as shipped (max, fma2, ex2, add2, +half ulp, PRMT)", "without the row-sum additions", "without the bf16 packing", "fma2 + ex2 only"};
+#define RUN_LOOP2(MODE)                                                                                         \
+  for (int threads = 128; threads <= 512; threads *= 2) {                                                       \
+    loop2_kernel<MODE><<<sms, threads>>>(out, cyc, 1, 64);                                                      \
+    CHECK(cudaDeviceSynchronize());                                                                             \
+    loop2_kernel<MODE><<<sms, threads>>>(out, cyc, 2, 64);                                                      \
+    CHECK(cudaDeviceSynchronize());                                                                             \
+    const double c = avg_cycles(cyc, sms);                                                                      \
+    printf("scheduled loop, %s, warps/SM %2d: %.2f weights/clk/SM (%.0f clk per 128-score block and warp)\n", modes[MODE], threads / 32, \
+           (double)threads * 64 * 128 / c, c / 64);                                                             \
+  }
+  RUN_LOOP2(0) RUN_LOOP2(1) RUN_LOOP2(2) RUN_LOOP2(3)
   printf("done\n");
   return 0;
 }

@@ -96,7 +96,7 @@ def test_tcgen05_gemm_vs_torch(variant, N, K, M):
 
 @pytest.mark.parametrize("lens", [[1, 2, 17, 64, 65, 128, 256, 300, 512, 33], [512], [300, 77], [130] * 4],
                          ids=["ragged10", "one512", "two", "four130"])
-@pytest.mark.parametrize("variant", [3, 2, 1, 0])
+@pytest.mark.parametrize("variant", [3, 0])
 def test_attention_vs_torch(variant, lens):
     """Every attention kernel against torch fp32 softmax(QK^T/sqrt(32))V per packed sequence; the short
     batches exercise the 128- and 64-query tiles the mma.sync kernel picks when few sequences are in flight."""
