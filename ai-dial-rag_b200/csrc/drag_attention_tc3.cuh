@@ -179,57 +179,33 @@ __device__ __forceinline__ void st_release_shared(int* p, int v) {
 }
 
 // ---- the softmax of one 128-key block of one row, scores in registers ----
-// PARTIAL (the last block of a sequence whose length is not a multiple of 128): only the 32-key chunks that contain a
-// key of the sequence are loaded / reduced / exponentiated (the rest of P is zero), keys beyond the sequence are masked.
-template <bool PARTIAL>
-__device__ __forceinline__ void load_scores(uint32_t s_tmem, int valid, uint32_t (&r)[TILE]) {
+__device__ __forceinline__ void load_scores(uint32_t s_tmem, uint32_t (&r)[TILE]) {
 #pragma unroll
-  for (int c = 0; c < TILE / 32; ++c)
-    if (!PARTIAL || c * 32 < valid) tc::tmem_ld32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
+  for (int c = 0; c < TILE / 32; ++c) tc::tmem_ld32(s_tmem + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
   tc::tmem_ld_wait();
 }
-template <bool PARTIAL>
-__device__ __forceinline__ float row_max(uint32_t (&r)[TILE], int valid) {
-  if (!PARTIAL) {
-    // eight independent chains of 3-input maxima
-    float mx[8];
+__device__ __forceinline__ float row_max(const uint32_t (&r)[TILE]) {
+  // eight independent chains of 3-input maxima
+  float mx[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) mx[c] = max3(__uint_as_float(r[3 * c]), __uint_as_float(r[3 * c + 1]), __uint_as_float(r[3 * c + 2]));
+  for (int c = 0; c < 8; ++c) mx[c] = max3(__uint_as_float(r[3 * c]), __uint_as_float(r[3 * c + 1]), __uint_as_float(r[3 * c + 2]));
 #pragma unroll
-    for (int i = 24; i + 15 < TILE; i += 16) {
+  for (int i = 24; i + 15 < TILE; i += 16) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) mx[c] = max3(mx[c], __uint_as_float(r[i + 2 * c]), __uint_as_float(r[i + 2 * c + 1]));
-    }
-    // 24 + 16 * 6 = 120: eight scores left
-#pragma unroll
-    for (int c = 0; c < 4; ++c) mx[c] = max3(mx[c], __uint_as_float(r[120 + 2 * c]), __uint_as_float(r[121 + 2 * c]));
-    return max3(max3(mx[0], mx[1], mx[2]), max3(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7]));
+    for (int c = 0; c < 8; ++c) mx[c] = max3(mx[c], __uint_as_float(r[i + 2 * c]), __uint_as_float(r[i + 2 * c + 1]));
   }
-  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  // 24 + 16 * 6 = 120: eight scores left
 #pragma unroll
-  for (int c = 0; c < TILE / 32; ++c) {
-    if (c * 32 < valid) {
-      if (valid < (c + 1) * 32) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i >= valid) r[c * 32 + i] = 0xff800000u;   // keys beyond the sequence
-      }
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) mx[j] = max3(mx[j], __uint_as_float(r[c * 32 + i + 2 * j]), __uint_as_float(r[c * 32 + i + 2 * j + 1]));
-      }
-    }
-  }
-  return max3(fmaxf(mx[0], mx[1]), mx[2], mx[3]);
+  for (int c = 0; c < 4; ++c) mx[c] = max3(mx[c], __uint_as_float(r[120 + 2 * c]), __uint_as_float(r[121 + 2 * c]));
+  return max3(max3(mx[0], mx[1], mx[2]), max3(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7]));
 }
 // p = 2^(s c - m c) as bf16 pairs (two per P column); returns the row sum of the unrounded weights
-template <bool PARTIAL>
+// (the 32-key chunks of a sequence's last block that hold no key of the sequence are skipped: their P columns are zero)
 __device__ __forceinline__ float exp_scores(const uint32_t (&r)[TILE], int valid, uint64_t scale2, uint64_t noff2, uint32_t (&pk)[TILE / 2]) {
   uint64_t l2a = pack_f32x2(0.f, 0.f), l2b = l2a;
 #pragma unroll
   for (int c = 0; c < TILE / 32; ++c) {
-    if (!PARTIAL || c * 32 < valid) {
+    if (c * 32 < valid) {
 #pragma unroll
       for (int i = c * 32; i < c * 32 + 32; i += 4) {
         float p0, p1, p2, p3;
@@ -330,7 +306,7 @@ template <bool TRACE = false>
 __global__ void __launch_bounds__(THREADS, 1)
 attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ ctx,
                      const int* __restrict__ cu_seqlens, int n_seq, int heads, int max_tiles, int n_stages, int split,
-                     float scale_log2, int stagger) {
+                     float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int hidden = heads * HEAD_DIM;
@@ -566,13 +542,6 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
       }
       pend = false;
     };
-    // The two groups do identical work: started together they stay in phase and meet at the MUFU pipe, each at half its
-    // rate, while the pipe idles during their (equally simultaneous) loads, maxima and waits.  Group 1 starts `stagger`
-    // clocks late; nothing pulls the groups back into phase, so the offset persists.
-    if (g == 1 && stagger > 0) {
-      const long long t0 = clock64();
-      while (clock64() - t0 < (long long)stagger) {}
-    }
     Cursor w;
     while (w.template seek<false, true>(g, split, published, desc, no_skip), !w.done) {
       float m = -INFINITY, l = 0.f;
@@ -588,7 +557,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
         }
         if (TRACE && tr) tr[1] = clock64();
         const bool partial = valid < TILE;   // (the same for every row of the tile)
-        load_scores<false>(s_tmem, valid, r);
+        load_scores(s_tmem, r);
         if (TRACE && tr) tr[2] = clock64();
         tc::tc_fence_before();
         __syncwarp();
@@ -598,7 +567,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
           for (int i = 0; i < TILE; ++i)
             if (i >= valid) r[i] = 0xff800000u;       // keys beyond the sequence
         }
-        const float mb = row_max<false>(r, valid);
+        const float mb = row_max(r);
         if (TRACE && tr) tr[3] = clock64() + (long long)(mb == 12345.f);   // (depends on the maximum: stamps after it)
         // the reference: block 0 sets it (key 0 is always valid: finite); later blocks raise it lazily
         float corr = 1.f;
@@ -614,7 +583,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
         const uint64_t noff2 = pack_f32x2(-off, -off);
         uint32_t pk[TILE / 2];
         // (a partial block skips the exponentials of the 32-key chunks that hold no key of the sequence)
-        const float lsum = exp_scores<true>(r, valid, scale2, noff2, pk);
+        const float lsum = exp_scores(r, valid, scale2, noff2, pk);
         if (TRACE && tr) tr[4] = clock64() + (long long)(pk[TILE / 2 - 1] == 0x12345678u);   // (after the last exponential)
         // One wait before P is stored.  Inside a job: the next block's scores S(k+1) -- issued after P(k-1) V by the same
         // thread, so P(k-1) V has retired as well.  At a job's last block: P(k-1) V itself.  Either way the P columns are

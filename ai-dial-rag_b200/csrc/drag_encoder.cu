@@ -304,7 +304,7 @@ struct drag_encoder {
   // 262144 tokens): QKV 0.255 vs 0.267 ms, FFN-up 0.365 vs 0.375, FFN-down 0.339 vs 0.397 in favour of pairs;
   // the out-projection (N = K = 384, epilogue-bound) 0.178 vs 0.202 in favour of single CTAs.  DRAG_GEMM_PAIRS=<mask>.
   int gemm_pairs = 15;
-  int attention_variant = 0;                      // 0 = mma.sync kernel, 3 / 4 = tcgen05 kernel (DRAG_ATTENTION)
+  int attention_variant = -1;                     // -1 = by sequence length (launch_attention), 0 = mma.sync kernel, 3 = tcgen05 kernel (DRAG_ATTENTION=mma / tc3)
   bool cls_only = true;                           // last layer on the [CLS] rows only (DRAG_CLS_ONLY=0: all rows)
   // optional per-kernel-class timing (bench.py roofline): event pairs recorded around the launches of the bulk workspace
   bool profiling = false;
@@ -432,6 +432,11 @@ int launch_gemm(const drag_encoder* e, const CUtensorMap& ta, const CUtensorMap&
 int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* qkv, bf16* ctx, const int32_t* d_cu,
                      int n_seq, int max_len, int heads, cudaStream_t st) {
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)HEAD_DIM);
+  // Default (-1): by the longest sequence of the batch.  Measured on B200, 12 heads (profiles/r02_attention_*): 512-token
+  // sequences 0.71 ms per 512 x 512 on tcgen05 against 0.83 ms on mma.sync; 256 tokens 0.40-0.43 against 0.39; 128 tokens
+  // 0.29-0.32 against 0.28 -- a softmax warp gets a MUFU.EX2 issued only every ~18 clocks, and the many small warps of
+  // the mma.sync kernel hide that better on short rows.
+  if (variant < 0) variant = max_len > 256 ? 3 : 0;
   if (variant == 3 || variant == 7) {
     // tcgen05, two softmax groups, P in tensor memory (drag_attention_tc3.cuh); variant 7 = the same with the debug timeline
     int sms = 148;
@@ -446,11 +451,10 @@ int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* q
     const int max_tiles = (max_len + attn3::TILE - 1) / attn3::TILE;
     const int grid = units < sms ? units : sms;
     const int stages = attn3::unit_stages(max_len);
-    static const int stagger = [] { const char* v = getenv("DRAG_ATTN_STAGGER"); return v ? atoi(v) : 0; }();   // clocks group 1 starts late
     if (variant == 7)
-      attn3::attention_tc3_kernel<true><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2, stagger);
+      attn3::attention_tc3_kernel<true><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2);
     else
-      attn3::attention_tc3_kernel<false><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2, stagger);
+      attn3::attention_tc3_kernel<false><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2);
   } else {
     const size_t smem = attn::smem_bytes(max_len);
     // few sequences (the query path): smaller query tiles so that the launch still fills the GPU
