@@ -254,7 +254,7 @@ __host__ __device__ inline size_t smem_bytes(int max_len) {
 
 __global__ void __launch_bounds__(WARPS * 32, 3)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx,
-                 const int* __restrict__ cu_seqlens, int heads, float scale_log2, int rows_per_cta) {
+                 const int* __restrict__ cu_seqlens, int heads, float scale_log2, int rows_per_cta, int len_lo, int len_hi) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int head = blockIdx.x % heads;
   const int q_tile = blockIdx.x / heads;
@@ -262,7 +262,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   const int tok0 = cu_seqlens[seq];
   const int S = cu_seqlens[seq + 1] - tok0;
   const int row0 = q_tile * rows_per_cta;
-  if (row0 >= S) return;
+  if (row0 >= S || S <= len_lo || S > len_hi) return;   // (len_lo, len_hi]: the length class this launch handles
   const int rows = min(S - row0, rows_per_cta);
   const int hidden = heads * HEAD_DIM;
   const int s_pad = (S + 31) & ~31;

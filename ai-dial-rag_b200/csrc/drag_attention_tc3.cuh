@@ -301,12 +301,13 @@ __device__ long long* g_trace = nullptr;
 
 // qkv : [T, 3*hidden] bf16 (tensor map: box 32 columns x 128 rows, 64-byte swizzle)
 // ctx : [T, hidden] bf16
-// grid = min(#SMs, units), block = THREADS, dynamic smem = smem_bytes(longest sequence)
+// grid = min(#SMs, units), block = THREADS, dynamic smem = smem_bytes(longest sequence); only sequences with
+// len_lo < length <= len_hi are processed
 template <bool TRACE = false>
 __global__ void __launch_bounds__(THREADS, 1)
 attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ ctx,
                      const int* __restrict__ cu_seqlens, int n_seq, int heads, int max_tiles, int n_stages, int split,
-                     float scale_log2) {
+                     float scale_log2, int len_lo, int len_hi) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int hidden = heads * HEAD_DIM;
@@ -370,6 +371,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
         const int S = __ldg(cu_seqlens + seq + 1) - tok0;
         const int n_tiles = (S + TILE - 1) / TILE;
         if (part >= n_tiles) continue;   // the unit has no jobs
+        if (S <= len_lo || S > len_hi) continue;   // another kernel's length class (mixed batches)
         const int n_q = (n_tiles - part + split - 1) / split;
         tc::mbar_wait(&kv_empty[stage], phase ^ 1);
         UnitDesc& d = desc[it % DESC_RING];

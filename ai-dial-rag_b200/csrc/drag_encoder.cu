@@ -22,6 +22,7 @@
 #include "drag_attention_tc3.cuh"
 #include "drag_common.cuh"
 #include "drag_gemm.cuh"
+#include "drag_mlp.cuh"
 
 namespace drag {
 namespace enc {
@@ -257,6 +258,7 @@ struct Layer {
   float *ln2_g, *ln2_b;                // this layer's output LayerNorm (used by the taps / the pooler)
   CUtensorMap tm_qkv, tm_o, tm_up, tm_down;
   CUtensorMap tp_qkv, tp_o, tp_up, tp_down;   // CTA-pair kernels: each CTA loads half of a W tile
+  CUtensorMap tf_w1, tf_w2;                   // fused feed-forward kernel: a CTA's half of a 64-unit chunk of W1 (32 rows) / W2 (96 rows)
 };
 
 }  // namespace enc
@@ -277,6 +279,7 @@ struct Workspace {
   CUtensorMap tm_x, tm_y, tm_ctx, tm_h;           // A-operand loads (128 x 64 boxes)
   CUtensorMap ts_x, ts_y, ts_qkv, ts_h;           // epilogue stores (32 x 64 boxes)
   CUtensorMap tm_qkv_heads;                       // attention loads: 128 tokens x one head (32 columns)
+  CUtensorMap t32_x, t32_y;                       // fused feed-forward kernel stores (32 rows x 16 columns, 32-byte swizzle)
   // host-buffer path
   cudaStream_t stream = nullptr;
   int32_t *d_ids = nullptr, *d_cu = nullptr;
@@ -305,6 +308,9 @@ struct drag_encoder {
   // the out-projection (N = K = 384, epilogue-bound) 0.178 vs 0.202 in favour of single CTAs.  DRAG_GEMM_PAIRS=<mask>.
   int gemm_pairs = 15;
   int attention_variant = -1;                     // -1 = by sequence length (launch_attention), 0 = mma.sync kernel, 3 = tcgen05 kernel (DRAG_ATTENTION=mma / tc3)
+  // FFN-up + GELU + FFN-down + residual in one kernel (drag_mlp.cuh) for batches of at least FUSED_MLP_MIN_TOKENS tokens;
+  // DRAG_FUSED_MLP=0: always the two GEMM kernels.  Measured (262 144 tokens): 0.52 ms against 0.33 + 0.33 ms.
+  bool fused_mlp = true;
   bool cls_only = true;                           // last layer on the [CLS] rows only (DRAG_CLS_ONLY=0: all rows)
   // optional per-kernel-class timing (bench.py roofline): event pairs recorded around the launches of the bulk workspace
   bool profiling = false;
@@ -313,7 +319,11 @@ struct drag_encoder {
   size_t prof_used = 0;
 };
 
-enum KernelClass { KC_EMBED = 0, KC_GEMM_QKV, KC_ATTENTION, KC_GEMM_OUT_LN, KC_GEMM_UP_GELU, KC_GEMM_DOWN_LN, KC_POOL, KC_CLS_TAIL, KC_COUNT };
+enum KernelClass { KC_EMBED = 0, KC_GEMM_QKV, KC_ATTENTION, KC_GEMM_OUT_LN, KC_GEMM_UP_GELU, KC_GEMM_DOWN_LN, KC_POOL, KC_CLS_TAIL, KC_MLP, KC_COUNT };
+
+// A pair of CTAs of the fused feed-forward kernel owns 256 tokens for 20 us: small batches (the query path) spread
+// better over the SMs as two GEMMs tiled over tokens AND columns.
+constexpr int FUSED_MLP_MIN_TOKENS = 8192;
 
 struct ProfScope {
   drag_encoder* e;
@@ -428,15 +438,49 @@ int launch_gemm(const drag_encoder* e, const CUtensorMap& ta, const CUtensorMap&
   return DRAG_OK;
 }
 
-// attention of every (sequence, head) of the packed batch
+// the fused feed-forward block (drag_mlp.cuh): out = gelu(LN_1(x) W1^T + b_1) W2^T + b_2 + LN_1(x), CTA pairs over 256-token tiles
+int launch_mlp(const drag_encoder* e, const CUtensorMap& tx, const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorMap& tout,
+               const mlp::MlpParams& p, cudaStream_t st) {
+  constexpr size_t smem = mlp::smem_bytes();
+  static std::once_flag once[16];
+  static cudaError_t attr_err[16];
+  const int dev_slot = e->device & 15;
+  std::call_once(once[dev_slot], [&] {
+    attr_err[dev_slot] = cudaFuncSetAttribute(mlp::mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (attr_err[dev_slot] == cudaSuccess) attr_err[dev_slot] = cudaFuncSetAttribute(mlp::mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  });
+  if (attr_err[dev_slot] != cudaSuccess)
+    return fail(DRAG_ERR_CUDA, "cudaFuncSetAttribute(mlp smem=%zu) failed: %s", smem, cudaGetErrorString(attr_err[dev_slot]));
+  const int tiles = (p.M + 2 * mlp::ROWS - 1) / (2 * mlp::ROWS);
+  const int pairs = e->sms / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
+  cfg.blockDim = dim3(mlp::THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (p.trace) DRAG_CUDA_OK(cudaLaunchKernelEx(&cfg, mlp::mlp_kernel<true>, tx, tw1, tw2, tout, p));
+  else DRAG_CUDA_OK(cudaLaunchKernelEx(&cfg, mlp::mlp_kernel<false>, tx, tw1, tw2, tout, p));
+  return DRAG_OK;
+}
+
+// Sequences longer than this go to the tcgen05 kernel, the others to the mma.sync kernel.  Measured on B200, 12 heads
+// (profiles/r02_attention_*): 512-token sequences 0.71 ms per 512 x 512 on tcgen05 against 0.83 ms on mma.sync; 256 tokens
+// 0.40-0.43 against 0.39; 128 tokens 0.29-0.32 against 0.28 -- a softmax warp gets a MUFU.EX2 issued only every ~18
+// clocks, and the many small warps of the mma.sync kernel hide that better on short rows.
+constexpr int ATTENTION_TC_ABOVE = 256;
+
+// attention of the (sequence, head) items of the packed batch whose length is in (len_lo, len_hi]; max_len = the longest
+// of those.  variant 0: mma.sync kernel, 3: tcgen05 kernel (7: with the debug timeline)
 int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* qkv, bf16* ctx, const int32_t* d_cu,
-                     int n_seq, int max_len, int heads, cudaStream_t st) {
+                     int n_seq, int max_len, int heads, cudaStream_t st, int len_lo = 0, int len_hi = 1 << 30) {
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)HEAD_DIM);
-  // Default (-1): by the longest sequence of the batch.  Measured on B200, 12 heads (profiles/r02_attention_*): 512-token
-  // sequences 0.71 ms per 512 x 512 on tcgen05 against 0.83 ms on mma.sync; 256 tokens 0.40-0.43 against 0.39; 128 tokens
-  // 0.29-0.32 against 0.28 -- a softmax warp gets a MUFU.EX2 issued only every ~18 clocks, and the many small warps of
-  // the mma.sync kernel hide that better on short rows.
-  if (variant < 0) variant = max_len > 256 ? 3 : 0;
   if (variant == 3 || variant == 7) {
     // tcgen05, two softmax groups, P in tensor memory (drag_attention_tc3.cuh); variant 7 = the same with the debug timeline
     int sms = 148;
@@ -452,9 +496,9 @@ int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* q
     const int grid = units < sms ? units : sms;
     const int stages = attn3::unit_stages(max_len);
     if (variant == 7)
-      attn3::attention_tc3_kernel<true><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2);
+      attn3::attention_tc3_kernel<true><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2, len_lo, len_hi);
     else
-      attn3::attention_tc3_kernel<false><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2);
+      attn3::attention_tc3_kernel<false><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2, len_lo, len_hi);
   } else {
     const size_t smem = attn::smem_bytes(max_len);
     // few sequences (the query path): smaller query tiles so that the launch still fills the GPU
@@ -463,7 +507,7 @@ int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* q
     const int q_tiles = (max_len + rows_per_cta - 1) / rows_per_cta;
     for (int s0 = 0; s0 < n_seq; s0 += 65535) {   // gridDim.y limit
       const int n = n_seq - s0 < 65535 ? n_seq - s0 : 65535;
-      attn::attention_kernel<<<dim3(heads * q_tiles, n), attn::WARPS * 32, smem, st>>>(qkv, ctx, d_cu + s0, heads, scale_log2, rows_per_cta);
+      attn::attention_kernel<<<dim3(heads * q_tiles, n), attn::WARPS * 32, smem, st>>>(qkv, ctx, d_cu + s0, heads, scale_log2, rows_per_cta, len_lo, len_hi);
     }
   }
   DRAG_CUDA_OK(cudaGetLastError());
@@ -498,11 +542,13 @@ int forward_impl(drag_encoder* e, Workspace& ws, const int32_t* d_ids, const int
   DRAG_REQUIRE(n_seq >= 0, "drag_encoder_forward: n_seq < 0");
   if (n_seq == 0) return DRAG_OK;
   DRAG_REQUIRE(h_cu[0] == 0, "drag_encoder_forward: cu_seqlens[0] must be 0");
-  int max_len = 0;
+  int max_len = 0, max_short = 0, n_long = 0;   // short / long: the two attention kernels' length classes
   for (int i = 0; i < n_seq; ++i) {
     const int len = h_cu[i + 1] - h_cu[i];
     DRAG_REQUIRE(len >= 1 && len <= e->shape.max_pos, "drag_encoder_forward: sequence %d has length %d (allowed 1..%d)", i, len, e->shape.max_pos);
     if (len > max_len) max_len = len;
+    if (len > ATTENTION_TC_ABOVE) ++n_long;
+    else if (len > max_short) max_short = len;
   }
   const int total = h_cu[n_seq];
   DRAG_REQUIRE((int64_t)total <= ws.max_tokens, "drag_encoder_forward: %d tokens exceed max_tokens=%lld", total, (long long)ws.max_tokens);
@@ -550,7 +596,16 @@ int forward_impl(drag_encoder* e, Workspace& ws, const int32_t* d_ids, const int
       p.M = n_seq;
     } else {
       ProfScope prof(e, ws, KC_ATTENTION, st);
-      rc = launch_attention(e->attention_variant, ws.tm_qkv_heads, ws.qkv, ws.ctx, d_cu, n_seq, max_len, sh.heads, st);
+      if (e->attention_variant >= 0) {
+        rc = launch_attention(e->attention_variant, ws.tm_qkv_heads, ws.qkv, ws.ctx, d_cu, n_seq, max_len, sh.heads, st);
+      } else {
+        // every sequence goes to the kernel of its length class whatever else is in the batch, so its embedding does not
+        // depend on the batch composition; a mixed batch takes two launches
+        rc = DRAG_OK;
+        if (n_long < n_seq) rc = launch_attention(0, ws.tm_qkv_heads, ws.qkv, ws.ctx, d_cu, n_seq, max_short, sh.heads, st, 0, ATTENTION_TC_ABOVE);
+        if (rc == DRAG_OK && n_long > 0)
+          rc = launch_attention(3, ws.tm_qkv_heads, ws.qkv, ws.ctx, d_cu, n_seq, max_len, sh.heads, st, ATTENTION_TC_ABOVE, 1 << 30);
+      }
       if (rc) return rc;
     }
     // mid_raw = ctx . Wo^T + b_o + LN_in(res_raw)   (+ row statistics of mid_raw)
@@ -561,6 +616,16 @@ int forward_impl(drag_encoder* e, Workspace& ws, const int32_t* d_ids, const int
       rc = (e->gemm_pairs & 2) ? DRAG_GEMM2_RES_WS(e, ws.tm_ctx, L.tp_o, *ts_mid, *ts_res, p, st) : DRAG_GEMM_RES(e, ws.tm_ctx, L.tm_o, *ts_mid, *ts_res, p, st);
     }
     if (rc) return rc;
+    if (e->fused_mlp && !last_cls && total >= FUSED_MLP_MIN_TOKENS) {
+      // res_raw = gelu(LN_1(mid) . W1^T + b_1) . W2^T + b_2 + LN_1(mid_raw)  (+ row statistics) in one kernel
+      mlp::MlpParams mp{};
+      mp.M = total; mp.up_c = L.up_c; mp.up_d = L.up_d; mp.down_cold = L.down_cold; mp.down_gamma = L.down_gamma;
+      mp.in_stats = mid_stats; mp.out_stats = res_stats; mp.inv_width = 1.0f / HIDDEN; mp.ln_eps = sh.ln_eps;
+      ProfScope prof(e, ws, KC_MLP, st);
+      rc = launch_mlp(e, *tm_mid, L.tf_w1, L.tf_w2, res == ws.x ? ws.t32_x : ws.t32_y, mp, st);
+      if (rc) return rc;
+      continue;
+    }
     // h = gelu(LN_1(mid) . W1^T + b_1)
     p.N = sh.inter; p.K = HIDDEN; p.colc = L.up_c; p.cold = L.up_d; p.gamma = nullptr; p.in_stats = mid_stats;
     p.residual = nullptr; p.out_stats = nullptr;
@@ -668,6 +733,8 @@ int init_workspace(drag_encoder* e, Workspace& ws, int64_t tokens, bool high_pri
   if ((rc = make_tmap(&ws.ts_qkv, ws.qkv, T, 3 * H, gemm::STORE_ROWS))) return rc;
   if ((rc = make_tmap(&ws.ts_h, ws.h, T, F, gemm::STORE_ROWS))) return rc;
   if ((rc = make_tmap_bf16_box(&ws.tm_qkv_heads, ws.qkv, T, 3 * H, attn3::TILE, attn3::HEAD_DIM))) return rc;
+  if ((rc = make_tmap_bf16_box(&ws.t32_x, ws.x, T, H, 32, mlp::STORE_COLS))) return rc;
+  if ((rc = make_tmap_bf16_box(&ws.t32_y, ws.y, T, H, 32, mlp::STORE_COLS))) return rc;
   // host-buffer path: own stream, pinned staging + device mirrors
   int lo = 0, hi = 0;
   DRAG_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = greatest priority (numerically lowest)
@@ -769,6 +836,8 @@ extern "C" int drag_encoder_create(const drag_bert_shape* shape, const float* co
     if ((rc = make_tmap(&L.tp_o, L.w_o, H, H, RES_BLOCK_N_PAIR / 2))) return bail(rc);
     if ((rc = make_tmap(&L.tp_up, L.w_up, F, H, FFN_BLOCK_N_PAIR / 2))) return bail(rc);
     if ((rc = make_tmap(&L.tp_down, L.w_down, H, F, RES_BLOCK_N_PAIR / 2))) return bail(rc);
+    if ((rc = make_tmap(&L.tf_w1, L.w_up, F, H, mlp::NC / 2))) return bail(rc);
+    if ((rc = make_tmap(&L.tf_w2, L.w_down, H, F, mlp::OUT_HALF / 2))) return bail(rc);
   }
   if ((rc = init_workspace(e, e->ws[0], e->max_tokens, false))) return bail(rc);
   if ((rc = init_workspace(e, e->ws[1], e->max_tokens < QUERY_WORKSPACE_TOKENS ? e->max_tokens : QUERY_WORKSPACE_TOKENS, true))) return bail(rc);
@@ -778,6 +847,8 @@ extern "C" int drag_encoder_create(const drag_bert_shape* shape, const float* co
     if (v && strcmp(v, "mma") == 0) e->attention_variant = 0;
     const char* gm = getenv("DRAG_GEMM_PAIRS");
     if (gm && gm[0] >= '0' && gm[0] <= '9') e->gemm_pairs = atoi(gm) & 31;
+    const char* fm = getenv("DRAG_FUSED_MLP");
+    if (fm && fm[0] == '0') e->fused_mlp = false;
     const char* co = getenv("DRAG_CLS_ONLY");
     if (co && co[0] == '0') e->cls_only = false;
   }
@@ -918,6 +989,51 @@ extern "C" int drag_debug_gemm(int device, int variant, const void* d_a, const v
     default:
       return fail(DRAG_ERR_INVALID, "drag_debug_gemm: unknown variant %d", variant);
   }
+}
+
+extern "C" int drag_debug_mlp(int device, const void* d_x, const void* d_in_stats, const void* d_w1g, const float* d_up_c,
+                              const float* d_up_d, const void* d_w2, const float* d_down_cold, const float* d_down_gamma,
+                              void* d_out, void* d_out_stats, int M, float ln_eps, void* stream) {
+  DRAG_REQUIRE(d_x && d_in_stats && d_w1g && d_up_c && d_up_d && d_w2 && d_down_cold && d_down_gamma && d_out && d_out_stats && M >= 1,
+               "drag_debug_mlp: bad arguments");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_debug_mlp: cannot select device %d", device);
+  drag_encoder fake{};
+  fake.device = device;
+  fake.sms = sm_count(device);
+  DRAG_REQUIRE(fake.sms >= 2, "drag_debug_mlp: cannot read the SM count of device %d", device);
+  mlp::MlpParams p{};
+  p.M = M; p.up_c = d_up_c; p.up_d = d_up_d; p.down_cold = d_down_cold; p.down_gamma = d_down_gamma;
+  p.in_stats = (const float2*)d_in_stats; p.out_stats = (float2*)d_out_stats; p.inv_width = 1.0f / HIDDEN; p.ln_eps = ln_eps;
+  if (const char* dbg = getenv("DRAG_MLP_DBG")) p.dbg = atoi(dbg);
+  CUtensorMap tx, tw1, tw2, tout;
+  int rc;
+  if ((rc = make_tmap(&tx, d_x, (uint64_t)M, HIDDEN, mlp::ROWS))) return rc;
+  if ((rc = make_tmap(&tw1, d_w1g, mlp::INTER, HIDDEN, mlp::NC / 2))) return rc;
+  if ((rc = make_tmap(&tw2, d_w2, HIDDEN, mlp::INTER, mlp::OUT_HALF / 2))) return rc;
+  if ((rc = make_tmap_bf16_box(&tout, d_out, (uint64_t)M, HIDDEN, 32, mlp::STORE_COLS))) return rc;
+  if (getenv("DRAG_MLP_TRACE")) {
+    // probes only: where CTA 0's MMA issuer and first epilogue warp spend their clocks
+    long long* d_trace = nullptr;
+    long long h[20];
+    DRAG_CUDA_OK(cudaMalloc((void**)&d_trace, sizeof(h)));
+    DRAG_CUDA_OK(cudaMemset(d_trace, 0, sizeof(h)));
+    p.trace = d_trace;
+    rc = launch_mlp(&fake, tx, tw1, tw2, tout, p, (cudaStream_t)stream);
+    if (rc == DRAG_OK && cudaStreamSynchronize((cudaStream_t)stream) == cudaSuccess &&
+        cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      const int tiles = (M + 2 * mlp::ROWS - 1) / (2 * mlp::ROWS), pairs = fake.sms / 2;
+      const int mine = (tiles + pairs - 1) / pairs;
+      fprintf(stderr, "mlp trace (clocks per tile of CTA 0, %d tiles): issuer total %lld | waits x_full %lld w1_full %lld w2_full %lld hp_full %lld out_free %lld || "
+              "epilogue warp total %lld | table+bar.sync %lld hacc_full wait %lld E1 body %lld residual copy + E2 %lld (E2: out_full wait %lld, "
+              "tensor-memory loads %lld, arithmetic %lld, staging + TMA store %lld, final store drain %lld)\n", mine,
+              h[7] / mine, h[0] / mine, h[1] / mine, h[2] / mine, h[3] / mine, h[4] / mine, h[15] / mine, h[8] / mine, h[9] / mine, h[10] / mine, h[11] / mine,
+              h[12] / mine, h[13] / mine, h[14] / mine, h[16] / mine, h[17] / mine);
+    }
+    cudaFree(d_trace);
+    return rc;
+  }
+  return launch_mlp(&fake, tx, tw1, tw2, tout, p, (cudaStream_t)stream);
 }
 
 extern "C" int drag_debug_attention(int device, int variant, const void* d_qkv, void* d_ctx, const int32_t* d_cu_seqlens,

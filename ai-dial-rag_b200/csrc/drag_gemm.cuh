@@ -129,6 +129,14 @@ __device__ __forceinline__ uint32_t gelu_f16x2(float x_lo, float x_hi) {
   return o;
 }
 
+// 16-byte shared-memory load (a pointer derived from the dynamic shared-memory base through casts is a GENERIC pointer
+// to the compiler: plain dereferences become LD.E instead of LDS)
+__device__ __forceinline__ float4 lds_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(tc::smem_u32(p)));
+  return v;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -440,8 +448,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const uint32_t* rw = reinterpret_cast<const uint32_t*>(rv);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 ga = *reinterpret_cast<const float4*>(tab0 + c + 4 * i);
-            const float4 cd = *reinterpret_cast<const float4*>(tab1 + c + 4 * i);
+            const float4 ga = lds_f4(tab0 + c + 4 * i);
+            const float4 cd = lds_f4(tab1 + c + 4 * i);
             const float g4[4] = {ga.x, ga.y, ga.z, ga.w};
             const float d4[4] = {cd.x, cd.y, cd.z, cd.w};
             float v[4];
@@ -462,8 +470,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const uint64_t nmu2 = pack_f32x2(-mu, -mu), rstd2 = pack_f32x2(rstd, rstd);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 cc = *reinterpret_cast<const float4*>(tab0 + c + 4 * i);
-            const float4 cd = *reinterpret_cast<const float4*>(tab1 + c + 4 * i);
+            const float4 cc = lds_f4(tab0 + c + 4 * i);
+            const float4 cd = lds_f4(tab1 + c + 4 * i);
             // v = rstd * (acc - mu * c) + d on fp32 pairs
             const uint64_t v01 = fma_f32x2(rstd2, fma_f32x2(nmu2, pack_f32x2(cc.x, cc.y), pack_f32x2(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]))),
                                            pack_f32x2(cd.x, cd.y));

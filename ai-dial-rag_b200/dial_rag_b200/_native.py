@@ -79,6 +79,7 @@ _SIGNATURES = {
     "drag_rows_to_chunks": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, _P, _P, _P]),
     "drag_debug_gemm": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int,
                                   C.c_float, C.c_float, _P]),
+    "drag_debug_mlp": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_float, _P]),
     "drag_debug_attention": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "drag_debug_attention_trace_words": (C.c_int, []),
     "drag_debug_set_attention_trace": (C.c_int, [C.c_int, _P]),

@@ -193,7 +193,7 @@ class B200Encoder:
 
     # ------------------------------------------------------------------ profiling (bench.py)
     KERNEL_CLASSES = ("embed_ln", "gemm_qkv", "attention", "gemm_out_ln", "gemm_up_gelu", "gemm_down_ln", "pool_normalize",
-                      "cls_tail")
+                      "cls_tail", "gemm_mlp_fused")
 
     def profile_begin(self, max_launches: int = 8192) -> None:
         _native.check(self.lib.drag_encoder_profile_begin(self._handle, int(max_launches)))

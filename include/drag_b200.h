@@ -122,9 +122,9 @@ int drag_encoder_forward_debug(drag_encoder* enc, const int32_t* d_ids, const in
 /*
  * Per-kernel-class device timing (CUDA events on the launch stream) for roofline reporting.
  * _begin arms up to max_launches event pairs; _end (after the caller synchronised the stream)
- * returns summed milliseconds and launch counts for the 8 classes
+ * returns summed milliseconds and launch counts for the 9 classes
  *   {embed+LN, QKV GEMM, attention, out-proj GEMM+LN, FFN-up GEMM+GELU, FFN-down GEMM+LN, pool,
- *    CLS-only tail of the last layer}.  Only forwards in the bulk workspace are recorded.
+ *    CLS-only tail of the last layer, fused feed-forward kernel}.  Only forwards in the bulk workspace are recorded.
  */
 /* Debug: phase timeline (clock64 stamps of CTA 0) of the tcgen05 attention kernel, see scripts/attn_trace.py. */
 int drag_debug_attention_trace_words(void);
@@ -253,9 +253,19 @@ int drag_debug_gemm(int device, int variant, const void* d_a, const void* d_w, c
                     void* d_out, void* d_out_stats, int M, int N, int K, float inv_width, float ln_eps,
                     void* stream);
 
+/*
+ * The fused feed-forward block (csrc/drag_mlp.cuh), bge-small shape only (384 -> 1536 -> 384):
+ *   out = gelu(LN_1(x) . W1^T + b_1) . W2^T + b_2 + LN_1(x)   (raw bf16 rows) and d_out_stats [M][3] partial (sum, sum^2)
+ * d_x bf16 [M,384] raw rows with d_in_stats [M][3]; d_w1g bf16 [1536,384] = gamma_1 (.) W1 with the folded terms
+ * d_up_c / d_up_d [1536]; d_w2 FP16 [384,1536]; d_down_cold = b_2 + beta_1, d_down_gamma = gamma_1 [384].
+ */
+int drag_debug_mlp(int device, const void* d_x, const void* d_in_stats, const void* d_w1g, const float* d_up_c,
+                   const float* d_up_d, const void* d_w2, const float* d_down_cold, const float* d_down_gamma,
+                   void* d_out, void* d_out_stats, int M, float ln_eps, void* stream);
+
 /* ctx[T, heads*32] = softmax(Q K^T / sqrt(32)) V per packed sequence; d_qkv is bf16 [n_tokens, 3*heads*32].
- * variant 0 = mma.sync kernel (the encoder's default), 1 = tcgen05 kernel (DRAG_ATTENTION=tc),
- * 2 = second tcgen05 design: ping-pong score tiles, four threads per row (DRAG_ATTENTION=tc2). */
+ * variant 0 = mma.sync kernel (what the encoder uses for sequences of up to 256 tokens), 3 = tcgen05 kernel (longer
+ * sequences; DRAG_ATTENTION=mma / tc3 force one for every length), 7 = 3 with the debug timeline. */
 int drag_debug_attention(int device, int variant, const void* d_qkv, void* d_ctx, const int32_t* d_cu_seqlens,
                          int n_seq, int n_tokens, int max_len, int heads, void* stream);
 

@@ -94,6 +94,59 @@ def test_tcgen05_gemm_vs_torch(variant, N, K, M):
         assert torch.allclose(out_stats[:, :parts], want, rtol=2e-4, atol=2e-2), (out_stats[:, :parts] - want).abs().max()
 
 
+@pytest.mark.parametrize("M", [256, 77, 1000, 20000, 40001])
+def test_fused_mlp_vs_torch(M):
+    """The fused feed-forward kernel (drag_mlp.cuh: FFN-up + GELU + FFN-down + residual LayerNorm in one launch, the
+    1536-wide intermediate stays in tensor memory) against plain torch fp32, and against the two separate GEMM
+    kernels it replaces."""
+    native, lib = _lib()
+    H, F = 384, 1536
+    g = torch.Generator(device="cuda").manual_seed(M + 5)
+    x = torch.randn(M, H, device="cuda", generator=g) * 1.5 + 0.3
+    x[:, 7] *= 12.0                                       # an outlier channel, as trained BERTs have
+    x = _bf16(x)
+    w1g = _bf16(torch.randn(F, H, device="cuda", generator=g) * 0.05)
+    up_c = w1g.float().sum(1).contiguous()                # the folded LayerNorm term c_n = sum_k W1g_nk
+    up_d = (torch.randn(F, device="cuda", generator=g) * 0.3).contiguous()
+    w2 = (torch.randn(H, F, device="cuda", generator=g) * 0.05).half()
+    cold = (torch.randn(H, device="cuda", generator=g) * 0.1).contiguous()
+    gamma = (torch.rand(H, device="cuda", generator=g) + 0.5).contiguous()
+    eps = 1e-12
+    stats = _row_stats(x)
+    mu = x.float().mean(1, keepdim=True)
+    rstd = torch.rsqrt(x.float().var(1, unbiased=False, keepdim=True) + eps)
+    out = torch.full((M, H), float("nan"), device="cuda", dtype=torch.bfloat16)
+    out_stats = torch.full((M, 3, 2), float("nan"), device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    native.check(lib.drag_debug_mlp(0, x.data_ptr(), stats.data_ptr(), w1g.data_ptr(), up_c.data_ptr(), up_d.data_ptr(),
+                                    w2.data_ptr(), cold.data_ptr(), gamma.data_ptr(), out.data_ptr(), out_stats.data_ptr(),
+                                    M, eps, stream))
+    torch.cuda.synchronize()
+    h = torch.nn.functional.gelu(rstd * (x.float() @ w1g.float().T - mu * up_c) + up_d)
+    ref = h @ w2.float().T + cold + (x.float() - mu) * rstd * gamma
+    got = out.float()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 0.01 * scale + 0.03, (M, err, scale)
+    assert (got - ref).abs().mean().item() <= 0.004 * max(ref.abs().mean().item(), 1e-3) + 2e-3
+    want = torch.stack([torch.stack((ref[:, i * 192:(i + 1) * 192].sum(1), (ref[:, i * 192:(i + 1) * 192] ** 2).sum(1)), 1)
+                        for i in range(2)], 1)
+    # (the statistics are taken from the kernel's own fp32 values: tanh-form GELU, fp16 intermediate)
+    assert torch.allclose(out_stats[:, :2], want, rtol=1e-3, atol=0.1), (out_stats[:, :2] - want).abs().max()
+    assert (out_stats[:, 2] == 0).all()
+    # ... and the unfused pair kernels on the same data (same rounding points: fp16 intermediate, bf16 output)
+    hbuf = torch.empty(M, F, device="cuda", dtype=torch.float16)
+    out2 = torch.empty(M, H, device="cuda", dtype=torch.bfloat16)
+    st2 = torch.zeros(M, 3, 2, device="cuda")
+    native.check(lib.drag_debug_gemm(0, 11, x.data_ptr(), w1g.data_ptr(), up_c.data_ptr(), up_d.data_ptr(), None,
+                                     stats.data_ptr(), None, hbuf.data_ptr(), None, M, F, H, 1.0 / H, eps, stream))
+    native.check(lib.drag_debug_gemm(0, 32, hbuf.data_ptr(), w2.data_ptr(), None, cold.data_ptr(), gamma.data_ptr(),
+                                     stats.data_ptr(), x.data_ptr(), out2.data_ptr(), st2.data_ptr(), M, H, F, 1.0 / H, eps, stream))
+    torch.cuda.synchronize()
+    assert (got - out2.float()).abs().max().item() <= 0.01 * scale + 0.03
+
+
 @pytest.mark.parametrize("lens", [[1, 2, 17, 64, 65, 128, 256, 300, 512, 33], [512], [300, 77], [130] * 4],
                          ids=["ragged10", "one512", "two", "four130"])
 @pytest.mark.parametrize("variant", [3, 0])
@@ -206,7 +259,11 @@ def test_layer_taps_vs_oracle(model):
                 ref = oenc.bert_hidden(w, tt, torch.ones_like(tt), shape)[0].numpy()
             g = got[cu[i]:cu[i + 1]]
             c = _cos(g, ref)
-            assert c.min() >= (0.99999 if layer == 0 else 0.999), (style, layer, i, float(c.min()))
+            # per-TOKEN cosine of an intermediate hidden state.  The outlier weights put five channels at +-100, where one
+            # bf16 ulp of the raw residual stream is 0.5, so a token's cosine after two layers sits around 0.999 whichever
+            # attention kernel ran (measured: 0.99894 with the mma.sync kernel, 0.9991 with the tcgen05 one)
+            bar = 0.99999 if layer == 0 else (0.998 if style == "outlier" else 0.999)
+            assert c.min() >= bar, (style, layer, i, float(c.min()))
             # bf16 activations through `layer` layers; the stress weights (6x larger Q/K, random LN affine) put the
             # noise of the deepest tap right at 0.15, so that one gets headroom -- the contract metric is the cosine
             # (the outlier weights carry five channels of +-100, where one bf16 ulp is 0.5 and every layer rounds the raw
@@ -281,8 +338,14 @@ def test_splits_large_batches_and_truncates(model):
     style, w, enc = model
     ids, cu = synth_token_batch(seed=2, n_seq=100, seq_len=256)  # 25600 tokens > max_tokens=16384
     got = enc.embed_packed(ids, cu)
-    first = enc.embed_packed(ids[: cu[10]], cu[:11])
-    assert np.array_equal(got[:10], first)
+    # bitwise equal whatever the batch is split into, as long as the feed-forward block runs in the same kernel class
+    # (batches of >= 8192 tokens: the fused kernel; below: the two GEMM kernels) ...
+    first = enc.embed_packed(ids[: cu[40]], cu[:41])
+    assert np.array_equal(got[:40], first)
+    # ... and equal to rounding noise across the two classes
+    small = enc.embed_packed(ids[: cu[10]], cu[:11])
+    assert _cos(small, got[:10]).min() >= 0.9999     # two bf16 pipelines with independent rounding: 1e-5 .. 5e-5 apart
+    assert np.abs(small - got[:10]).max() <= 3e-3
     long = [101] + list(range(1000, 1700)) + [102]  # 702 tokens -> truncated to 512 keeping [SEP]
     emb = enc.embed_token_lists([long])
     want = oenc.encode_token_lists(w, [long])
