@@ -25,8 +25,14 @@
 // The residual rows LN_1(X) of E2 are the X rows themselves: every epilogue thread copies its row's 192 values from the
 // X tile into registers before the tile is released (chunk 20), so the next tile's X streams in under the last chunks.
 //
-// CTA = 10 warps: warp 0 TMA producer, warp 1 MMA issuer (pair leader only), warps 2-9 epilogue (thread = token row,
-// warps 2-5 / 6-9 take the two column halves).
+// CTA = 20 warps in five warpgroups with their own register budgets (setmaxnreg):
+//   warps 0-3    warp 0 TMA producer, warp 1 MMA issuer (pair leader only), two idle                       64 registers
+//   warps 4-11   epilogue class A: E1 on hidden units [0, 32) of every chunk (16 per warp) and all of E2   160 registers
+//                (thread = token row; warps 4-7 / 8-11 take output columns [0, 192) / [192, 384))
+//   warps 12-19  epilogue class B: E1 on hidden units [32, 64) of every chunk                               48 registers
+// E1's instruction mix (per 32 elements: 112 half2 FMA-pipe, 32 MUFU.TANH, 32 FFMA2, 16 F2FP, measured) runs pipe after
+// pipe in a single warp; four warps per scheduler interleave the pipes, two did not (1 560 clocks per chunk against a
+// MUFU floor of 512: profiles/r02_mlp_*).
 #pragma once
 
 #include <cuda_bf16.h>
@@ -50,8 +56,11 @@ constexpr int OUT_HALF = HIDDEN / 2;             // 192 output columns per G2 in
 constexpr int W2_HALF_BYTES = (OUT_HALF / 2) * 128;   // 12 KB: this CTA's 96 rows of one output half, the chunk's 64 k
 constexpr int W2_BYTES = 2 * W2_HALF_BYTES;      // 24 KB
 constexpr int W_SLOT_BYTES = W1_BYTES + W2_BYTES;
-constexpr int EPI_WARPS = 8;
-constexpr int THREADS = 64 + 32 * EPI_WARPS;
+constexpr int EPI_WARPS = 8;                     // class A (E1 + E2); class B adds another 8 for E1
+constexpr int E1_WARPS = 16;
+constexpr int THREADS = 128 + 32 * E1_WARPS;     // 640
+constexpr int REGS_CONTROL = 64, REGS_A = 160, REGS_B = 48;   // 128 x 64 + 256 x 160 + 256 x 48 = 61 440 = 640 x 96: the CTA can only redistribute what it was launched with
+constexpr int E1_COLS = NC / 4;                  // 16 hidden units per E1 warp and chunk
 constexpr int STORE_COLS = 16;                   // E2 works in steps of 16 output columns
 constexpr int STAGING_BYTES = 2048;              // per epilogue warp: two [32 rows][16 columns] bf16 boxes (32-byte swizzle)
 constexpr int BAR_BYTES = 256;
@@ -77,7 +86,7 @@ struct MlpParams {
   float2* out_stats;           // [M][STATS_PARTS] of the OUT rows
   float inv_width, ln_eps;
   long long* trace;            // TRACE instantiation (DRAG_MLP_TRACE): clock sums of the waits of CTA 0's issuer [0..7] and first epilogue warp [8..19]
-  int dbg;                     // probes only (DRAG_MLP_DBG): 1 = E1 without the LayerNorm fold / GELU arithmetic, 2 = E1 without the tensor-memory load as well
+  int dbg;                     // probes only (DRAG_MLP_DBG): 1 = E1 without the LayerNorm fold / GELU arithmetic, 2 = E1 without the tensor-memory load as well, 4 = G1 strictly two chunks ahead across tile boundaries
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -96,6 +105,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};"
+               ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(taddr)
+               : "memory");
 }
 // D[tmem of both CTAs] (+)= A[tmem: 16-bit pairs, one column per two k] . B[smem desc] over a CTA pair
 __device__ __forceinline__ void umma_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -134,7 +148,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ C
   uint64_t* w2_full = bars + 6;       // [2] leader
   uint64_t* w2_empty = bars + 8;      // [2]
   uint64_t* hacc_full = bars + 10;    // [2] G1(c) has retired
-  uint64_t* hp_full = bars + 12;      // [2] leader: the 16 epilogue warps of the pair have written h(c)
+  uint64_t* hp_full = bars + 12;      // [2] leader: the 32 E1 warps of the pair have written h(c)
   uint64_t* out_full = bars + 14;     // G2 of the tile's last chunk has retired
   uint64_t* out_free = bars + 15;     // leader: the 16 epilogue warps have read OUT
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
@@ -163,7 +177,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ C
       tc::mbar_init(&w2_full[b], 1);
       tc::mbar_init(&w2_empty[b], 1);
       tc::mbar_init(&hacc_full[b], 1);
-      tc::mbar_init(&hp_full[b], 2 * EPI_WARPS);
+      tc::mbar_init(&hp_full[b], 2 * E1_WARPS);
     }
     tc::mbar_init(out_full, 1);
     tc::mbar_init(out_free, 2 * EPI_WARPS);
@@ -188,7 +202,54 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ C
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == 0) {
+  // E1 of one warp: its 16 hidden units of chunk g.  h = gelu(rstd * (acc - mu * colc) + cold) as fp16 pairs, written over the
+  // first 8 of the 16 accumulator columns just read: the A operand of G2's k-step `cg`
+  auto e1_chunk = [&](int g, int cg, uint32_t lane_base, uint32_t leader_hp_full, float mu, float rstd) {
+    const int c = g % CHUNKS, b = g & 1;
+    const float* tab_c = tab1 + c * NC + cg * E1_COLS;
+    const float* tab_d = tab_c + INTER;
+    tc::mbar_wait(&hacc_full[b], (uint32_t)(g >> 1) & 1);
+    tc::tc_fence_after();
+    const uint32_t t_h = lane_base + (uint32_t)(HACC_COL + b * NC + cg * E1_COLS);
+    uint32_t r[16];
+    if (!(p.dbg & 2)) {
+      tmem_ld16(t_h, r);
+      tc::tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = 0x3c000000u + (uint32_t)i;
+    }
+    uint32_t o[8];
+    if (p.dbg & 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (r[2 * i] >> 16) | (r[2 * i + 1] & 0xffff0000u);
+    } else {
+      const uint64_t nmu2 = gemm::pack_f32x2(-mu, -mu), rstd2 = gemm::pack_f32x2(rstd, rstd);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 cc = gemm::lds_f4(tab_c + 4 * i);
+        const float4 cd = gemm::lds_f4(tab_d + 4 * i);
+        const uint64_t v01 = gemm::fma_f32x2(rstd2, gemm::fma_f32x2(nmu2, gemm::pack_f32x2(cc.x, cc.y), gemm::pack_f32x2(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]))),
+                                             gemm::pack_f32x2(cd.x, cd.y));
+        const uint64_t v23 = gemm::fma_f32x2(rstd2, gemm::fma_f32x2(nmu2, gemm::pack_f32x2(cc.z, cc.w), gemm::pack_f32x2(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]))),
+                                             gemm::pack_f32x2(cd.z, cd.w));
+        float v0, v1, v2, v3;
+        gemm::unpack_f32x2(v01, v0, v1);
+        gemm::unpack_f32x2(v23, v2, v3);
+        o[2 * i] = gemm::gelu_f16x2(v0, v1);
+        o[2 * i + 1] = gemm::gelu_f16x2(v2, v3);
+      }
+    }
+    tmem_st8(t_h, o);
+    tc::tmem_st_wait();
+    tc::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive_cluster(leader_hp_full + (uint32_t)(b * 8));
+  };
+
+  if (warp < 4) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONTROL));
+   if (warp == 0) {
     // ===================== TMA producer: this CTA's rows of X, its halves of the weight chunks =====================
     if (tc::elect_one()) {
       const uint32_t bar_x = tc::mapa_shared(tc::smem_u32(x_full), 0);
@@ -215,7 +276,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ C
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+   } else if (warp == 1) {
     // ===================== MMA issuer (pair leader):  G1(0) G1(1) | G2(0) G1(2) | G2(1) G1(3) | ... =====================
     if (rank == 0 && tc::elect_one()) {
       constexpr uint32_t idesc1 = tc::umma_idesc_bf16(2 * ROWS, NC);
@@ -263,9 +324,9 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ C
           const uint64_t b_desc = tc::umma_desc_sw128(w_addr + (uint32_t)(b * W_SLOT_BYTES + W1_BYTES + j * W2_HALF_BYTES));
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            // h of hidden units [16 kk, 16 kk + 16): 8 packed columns; each column half keeps its 16 packed columns at
-            // the start of the 32 accumulator columns it was computed from
-            const uint32_t a_tmem = tmem_base + (uint32_t)(HACC_COL + b * NC + (kk >> 1) * 32 + (kk & 1) * 8);
+            // h of hidden units [16 kk, 16 kk + 16): 8 packed columns at the start of the 16 accumulator columns they were
+            // computed from (one E1 warp per lane quarter wrote them)
+            const uint32_t a_tmem = tmem_base + (uint32_t)(HACC_COL + b * NC + kk * E1_COLS);
             umma_ts_pair(tmem_base + (uint32_t)(OUT_COL + j * OUT_HALF), a_tmem, b_desc + (uint64_t)(kk * 2), idesc2, (c | kk) != 0 ? 1u : 0u);
           }
         }
@@ -277,6 +338,13 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ C
         g1(1);
         for (int g = 0; g < total; ++g) {
           g2(g);
+          // G1 runs two chunks ahead; the first two G1 of the NEXT tile wait for its X rows, which can only be loaded once
+          // this tile's last G1 has retired: they go out after this tile's last G2, so that E2 starts in the meantime
+          const int c = g % CHUNKS;
+          if (!(p.dbg & 4)) {
+            if (c == CHUNKS - 2) continue;
+            if (c == CHUNKS - 1 && g + 1 < total) g1(g + 1);
+          }
           if (g + 2 < total) g1(g + 2);
         }
       }
@@ -286,11 +354,30 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ C
       }
     }
     __syncwarp();
+   }
+  } else if (warp >= 4 + EPI_WARPS) {
+    // ===================== epilogue class B: E1 only =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_B));
+    const int quarter = warp & 3;
+    const int cg = 2 + ((warp - 4 - EPI_WARPS) >> 2);
+    const int row_in_tile = quarter * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t leader_hp_full = tc::mapa_shared(tc::smem_u32(&hp_full[0]), 0);
+    float mu = 0.f, rstd = 0.f;
+    for (int g = 0; g < total; ++g) {
+      const int it = g / CHUNKS;
+      if (g - it * CHUNKS == 0) {
+        const int row = (pair + it * n_pairs) * 2 * ROWS + (int)rank * ROWS + row_in_tile;
+        gemm::row_stats(p.in_stats, row, row < p.M, p.inv_width, p.ln_eps, mu, rstd);
+      }
+      e1_chunk(g, cg, lane_base, leader_hp_full, mu, rstd);
+    }
   } else {
-    // ===================== epilogue: E1 per chunk, E2 per tile =====================
-    const int ew = warp - 2;
+    // ===================== epilogue class A: E1 per chunk, E2 per tile =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_A));
+    const int ew = warp - 4;
     const int quarter = warp & 3;             // TMEM lanes this warp may touch: [32 * quarter, +32)
-    const int half = ew >> 2;                 // column half: 32 of a chunk's 64 hidden units, 192 of the 384 output columns
+    const int half = ew >> 2;                 // E1: hidden units [16 half, +16) of every chunk; E2: output columns [192 half, +192)
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t leader_hp_full = tc::mapa_shared(tc::smem_u32(&hp_full[0]), 0);
@@ -397,54 +484,15 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ C
     };
 
     for (int g = 0; g < total; ++g) {
-      const int it = g / CHUNKS, c = g - it * CHUNKS, b = g & 1;
+      const int it = g / CHUNKS, c = g - it * CHUNKS;
       if (c == 0) {
         if (it > 0) { mu_out = mu; rstd_out = rstd; }
         tile_stats(it, mu, rstd);
       }
-      const float* tab_c = tab1 + c * NC + half * 32;
-      const float* tab_d = tab_c + INTER;
       long long t0 = (TRACE && tr) ? clock64() : 0;
-
-      tc::mbar_wait(&hacc_full[b], (uint32_t)(g >> 1) & 1);
-      tc::tc_fence_after();
-      if (TRACE && tr) { const long long t1 = clock64(); te[1] += t1 - t0; t0 = t1; }
-      const uint32_t t_h = lane_base + (uint32_t)(HACC_COL + b * NC + half * 32);
-      uint32_t r[32];
-      if (!(p.dbg & 2)) {
-        tc::tmem_ld32(t_h, r);
-        tc::tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = 0x3c000000u + (uint32_t)i;
-      }
-      uint32_t o[16];
-      if (p.dbg & 1) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) o[i] = (r[2 * i] >> 16) | (r[2 * i + 1] & 0xffff0000u);
-      } else {
-        const uint64_t nmu2 = gemm::pack_f32x2(-mu, -mu), rstd2 = gemm::pack_f32x2(rstd, rstd);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 cc = gemm::lds_f4(tab_c + 4 * i);
-          const float4 cd = gemm::lds_f4(tab_d + 4 * i);
-          const uint64_t v01 = gemm::fma_f32x2(rstd2, gemm::fma_f32x2(nmu2, gemm::pack_f32x2(cc.x, cc.y), gemm::pack_f32x2(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]))),
-                                               gemm::pack_f32x2(cd.x, cd.y));
-          const uint64_t v23 = gemm::fma_f32x2(rstd2, gemm::fma_f32x2(nmu2, gemm::pack_f32x2(cc.z, cc.w), gemm::pack_f32x2(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]))),
-                                               gemm::pack_f32x2(cd.z, cd.w));
-          float v0, v1, v2, v3;
-          gemm::unpack_f32x2(v01, v0, v1);
-          gemm::unpack_f32x2(v23, v2, v3);
-          o[2 * i] = gemm::gelu_f16x2(v0, v1);
-          o[2 * i + 1] = gemm::gelu_f16x2(v2, v3);
-        }
-      }
-      // h(c) as the A operand of G2(c): 16 packed columns over the first half of the 32 columns just read
-      tmem_st16(t_h, o);
-      tc::tmem_st_wait();
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive_cluster(leader_hp_full + (uint32_t)(b * 8));
+      if (c == 0 && it > 0) finish_tile(it - 1);   // G2 of the previous tile's last chunk is issued before this chunk's G1
+      if (TRACE && tr) { const long long t1 = clock64(); te[3] += t1 - t0; t0 = t1; }
+      e1_chunk(g, half, lane_base, leader_hp_full, mu, rstd);
       if (TRACE && tr) { const long long t1 = clock64(); te[2] += t1 - t0; t0 = t1; }
 
       if (c == RES_CHUNK) {
@@ -460,8 +508,6 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ C
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(x_empty);
       }
-      if (c == 0 && it > 0) finish_tile(it - 1);
-      if (TRACE && tr) { const long long t1 = clock64(); te[3] += t1 - t0; }
     }
     if (my_tiles > 0) {
       mu_out = mu;

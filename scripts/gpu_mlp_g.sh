@@ -1,7 +1,7 @@
 #!/bin/bash
 # whole tree after the fused feed-forward kernel: GPU test suite, threshold probe, default bench
 mkdir -p gpurun_out
-for t in 8192 4096 2048; do timeout 120 python scripts/mlp_probe.py --tokens $t --iters 50 2>&1 | tail -n 2; done
+for t in 12288; do timeout 120 python scripts/mlp_probe.py --tokens $t --iters 50 2>&1 | tail -n 2; done
 echo "=== pytest -m gpu"
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/g_pytest_gpu.log 2>&1; echo "exit=$?"; grep -v "^drag_b200" gpurun_out/g_pytest_gpu.log | tail -n 8
 echo "=== smoke"
