@@ -243,7 +243,11 @@ def test_errors_are_python_exceptions():
     dm = DeviceMatrix(synth_matrix(seed=1, rows=5000, dim=384))
     with pytest.raises(ValueError):
         dm.topk(np.zeros((1, 100)), 5, "inner_product")
+    # k beyond the kernels' list capacity is not an error (the reference takes any limit): it goes through the
+    # distances + stable sort path (tests/test_scale_and_threads_gpu.py checks its ids)
+    dist, rows, count = dm.topk(np.zeros((1, 384)), 5000, "inner_product")
+    assert count.tolist() == [5000] and np.array_equal(rows[0][:5000], np.arange(5000))   # all scores equal: row order
     with pytest.raises(DragError):
-        dm.topk(np.zeros((1, 384)), 5000, "inner_product")
+        dm.topk(np.zeros((1, 384)), 0, "inner_product")
     with pytest.raises(ValueError):
         dm.topk(np.zeros((1, 384)), 5, "manhattan")
