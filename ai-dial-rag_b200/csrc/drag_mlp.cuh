@@ -32,7 +32,7 @@
 //   warps 12-19  epilogue class B: E1 on hidden units [32, 64) of every chunk                               48 registers
 // E1's instruction mix (per 32 elements: 112 half2 FMA-pipe, 32 MUFU.TANH, 32 FFMA2, 16 F2FP, measured) runs pipe after
 // pipe in a single warp; four warps per scheduler interleave the pipes, two did not (1 560 clocks per chunk against a
-// MUFU floor of 512: profiles/r02_mlp_*).
+// MUFU floor of 512: profiles/r02_mlp_development.txt).
 #pragma once
 
 #include <cuda_bf16.h>

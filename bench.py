@@ -786,11 +786,12 @@ def main() -> None:
                   "(FFN-up + GELU + FFN-down + residual fused, the 1536-wide intermediate stays in tensor memory)",
         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
         "frac": achieved / peaks["tflops_sustained"],
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the four instantiations, from the
-        # ncu --set full capture in profiles/r01_e_ncu_full_summary.md (taken at 65 536 tokens, scaled by tokens)
-        "traffic": 191.3e6 * tokens / 65536.0,
-        "traffic_source": "profiles/r01_e_ncu_full_summary.md (ncu --set full, 65 536 tokens, scaled linearly in tokens); "
-                          "algorithmic operand+output bytes per launch average 906 MB at 262 144 tokens",
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, launch-weighted mean over the step's GEMM-class launches, from
+        # the ncu --set full captures in profiles/r02_k_ncu_full_summary.md: mlp_kernel 375 MB (measured at 262 144 tokens),
+        # QKV 146 MB and out-projection 123.5 MB at 65 536 tokens (x4: an upper bound on what L2 retention hides there)
+        "traffic": 487.0e6 * tokens / 262144.0,
+        "traffic_source": "profiles/r02_k_ncu_full_summary.md (ncu --set full; scaled linearly in tokens); algorithmic "
+                          "operand+output bytes per launch average 611 MB at 262 144 tokens",
         "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
         "flop_per_launch": gemm_flop / gemm_launches, "avg_launch_ms": gemm_ms / gemm_launches,
         "share_of_step": gemm_ms / kernel_ms,
