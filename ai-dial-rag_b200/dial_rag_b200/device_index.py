@@ -136,7 +136,7 @@ class DeviceMatrix:
             return self._batch_state
         torch = _torch()
         dev = self.matrix.device
-        state = {"ok": False}
+        state = {"ok": False, "cos_ok": False}   # wide rows (D > 512: description / multimodal retrievers): float64 scan only
         if self.dim % 64 == 0 and self.dim <= BATCH_MAX_DIM and 0 < self.n_rows < 2 ** 31:
             stream = torch.cuda.current_stream(dev).cuda_stream
             inv = torch.empty(self.n_rows, dtype=torch.float32, device=dev)

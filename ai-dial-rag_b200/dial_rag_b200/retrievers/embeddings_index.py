@@ -301,14 +301,17 @@ def _get_page_index(chunk: Chunk) -> int:
     return chunk.metadata["page_number"] - 1
 
 
+try:  # resolved once: a failing import per call cost 50 us x 1M chunks in pack_embedding_matrix (bench extra.index_build)
+    from docarray.typing import NdArray as _NdArray  # type: ignore
+except Exception:  # noqa: BLE001
+    _NdArray = None
+
+
 def to_ndarray(arr: np.ndarray):
     """Wrap as docarray ``NdArray`` when docarray is present (embeddings_index.py:97-98)."""
-    try:
-        from docarray.typing import NdArray  # type: ignore
-
-        return NdArray(shape=arr.shape, buffer=arr, dtype=arr.dtype)
-    except Exception:  # noqa: BLE001
+    if _NdArray is None:
         return arr
+    return _NdArray(shape=arr.shape, buffer=arr, dtype=arr.dtype)
 
 
 def _rows_of(item) -> np.ndarray:

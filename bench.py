@@ -462,6 +462,75 @@ def bench_text_path(torch, device, weights, n_texts: int = 1024, steps: int = 5)
     }
 
 
+def bench_index_build(torch, device, rows: int = 1_000_000, generic_rows: int = 100_000):
+    """embeddings of `rows` chunks -> persisted MultiEmbeddings -> DocIndex -> device-resident index
+    (upload, bit-exact row norms, bf16 scoring copy).  The matrix path is what build_embeddings produces
+    (pack_embedding_matrix: zero-copy views, O(1) flatten); the generic path is the reference's per-item format
+    (pack_simple_embeddings + the flatten loop, as for records deserialised from storage)."""
+    from dial_rag_b200.records import RetrievalType
+    from dial_rag_b200.retrievers.embeddings_index import (EmbeddingsIndex, create_index_by_chunk, pack_embedding_matrix,
+                                                           pack_simple_embeddings)
+
+    rng = np.random.default_rng(11)
+    emb = rng.standard_normal((rows, HIDDEN), dtype=np.float32)
+    t0 = time.perf_counter()
+    multi = pack_embedding_matrix(emb)
+    t1 = time.perf_counter()
+    doc = create_index_by_chunk(multi)
+    t2 = time.perf_counter()
+    index = EmbeddingsIndex(RetrievalType.TEXT, [doc], limit=20)
+    index.find(emb[0].astype(np.float64))          # first use uploads the matrix
+    torch.cuda.synchronize(device)
+    t3 = time.perf_counter()
+    g0 = time.perf_counter()
+    gdoc = create_index_by_chunk(pack_simple_embeddings(list(emb[:generic_rows])))
+    g1 = time.perf_counter()
+    assert np.array_equal(gdoc.embeddings, emb[:generic_rows])
+    out = {
+        "workload": f"{rows} x {HIDDEN} float32 chunk embeddings -> MultiEmbeddings -> DocIndex -> resident device index + first query",
+        "pack_s": t1 - t0, "flatten_s": t2 - t1, "upload_and_first_query_s": t3 - t2,
+        "chunks_per_s": rows / (t3 - t0),
+        "generic_item_path_chunks_per_s": generic_rows / (g1 - g0),
+        "note": "pack = one ItemEmbeddings view per chunk (host Python); flatten is O(1) for the matrix path",
+    }
+    del index, doc, multi, emb
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_wide_dims(torch, device, peaks, rows: int = 250_000):
+    """the other consumers of the index (description / multimodal retrievers) use D = 1024 / 1408,
+    beyond the tensor-core batch path (D <= 512): they run on the float64 scan."""
+    from dial_rag_b200.device_index import DeviceMatrix
+
+    out = {}
+    for dim in (1024, 1408):
+        g = torch.Generator(device=device).manual_seed(dim)
+        mat = torch.randn((rows, dim), generator=g, device=device)
+        dm = DeviceMatrix(mat)
+        res = {}
+        for nq in (1, 16):
+            q = torch.randn((nq, dim), generator=g, device=device, dtype=torch.float32).double()
+            for _ in range(3):
+                dm.topk_device(q, 20, "cosine_sim")
+            torch.cuda.synchronize(device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                dm.topk_device(q, 20, "cosine_sim")
+            e1.record()
+            torch.cuda.synchronize(device)
+            ms = e0.elapsed_time(e1) / 20
+            passes = -(-nq // 4)
+            res[f"q{nq}"] = {"ms": ms, "queries_per_s": nq / (ms / 1e3), "matrix_passes": passes,
+                             "hbm_frac": passes * rows * dim * 4 / (ms / 1e3) / 1e9 / peaks["hbm_gbs"]}
+        out[f"d{dim}"] = res
+        del dm, mat
+        torch.cuda.empty_cache()
+    out["workload"] = f"exact top-20 cosine, {rows} rows fp32, float64 scan (drag_topk): 1 query and 16 queries per call"
+    return out
+
+
 def bench_search_sharded(torch, dist, device, rank, world, peaks, rows_per_gpu: int, n_queries: int, k: int, steps: int, warmup: int):
     """configs[3] shape: bf16 index row-sharded over the GPUs, replicated queries, one NCCL all-gather of
     the per-shard top-k candidates + drag_topk_merge on every rank.  Parity inside the run: the first
@@ -907,6 +976,16 @@ def main() -> None:
             roofline["query_batch256_qps_device"] = qp["batch256"]["queries_per_s_device"]
             line["extra"]["text_path"] = bench_text_path(torch, device, weights)
             line["e2e"]["text_to_embedding_chunks_per_s"] = line["extra"]["text_path"]["chunks_per_s_build_embeddings"]
+            wide = bench_wide_dims(torch, device, peaks)
+            line["extra"]["search_wide_dims"] = wide
+            for dname in ("d1024", "d1408"):
+                roofline[f"search_{dname}_single_250k_ms"] = wide[dname]["q1"]["ms"]
+                roofline[f"search_{dname}_single_250k_hbm_frac"] = wide[dname]["q1"]["hbm_frac"]
+                roofline[f"search_{dname}_q16_250k_ms"] = wide[dname]["q16"]["ms"]
+            ib = bench_index_build(torch, device)
+            line["extra"]["index_build"] = ib
+            line["e2e"]["index_build_chunks_per_s_1m"] = ib["chunks_per_s"]
+            line["e2e"]["index_build_generic_item_path_chunks_per_s"] = ib["generic_item_path_chunks_per_s"]
         except Exception as exc:  # noqa: BLE001 - the secondary metric must not lose the headline line
             line["extra"]["search_error"] = repr(exc)
 

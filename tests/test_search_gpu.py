@@ -247,7 +247,30 @@ def test_errors_are_python_exceptions():
     # distances + stable sort path (tests/test_scale_and_threads_gpu.py checks its ids)
     dist, rows, count = dm.topk(np.zeros((1, 384)), 5000, "inner_product")
     assert count.tolist() == [5000] and np.array_equal(rows[0][:5000], np.arange(5000))   # all scores equal: row order
-    with pytest.raises(DragError):
-        dm.topk(np.zeros((1, 384)), 0, "inner_product")
+    dist, rows, count = dm.topk(np.zeros((1, 384)), 0, "inner_product")   # limit 0: empty, as argsort()[:0]
+    assert rows.shape == (1, 0) and count.tolist() == [0]
+    import torch
+
+    with pytest.raises(DragError):   # the device-tensor entry point validates k itself
+        dm.topk_device(torch.zeros((1, 384), dtype=torch.float64, device="cuda"), 0, "inner_product")
     with pytest.raises(ValueError):
         dm.topk(np.zeros((1, 384)), 5, "manhattan")
+
+
+@pytest.mark.parametrize("dim", [1024, 1408])
+@pytest.mark.parametrize("metric", ["cosine_sim", "sqeuclidean_dist"])
+def test_wide_rows_many_queries(dim, metric):
+    """D = 1024 / 1408 (the description and multimodal retrievers' embeddings) with more queries than the
+    batched path's threshold: beyond its D <= 512 they must go through the float64 scan, ids bit-exact vs the oracle."""
+    from dial_rag_b200.device_index import DeviceMatrix
+
+    m = synth_matrix(seed=dim, rows=70_001, dim=dim, normalise=False)
+    q = synth_queries(seed=dim + 1, n=9, dim=dim)
+    dm = DeviceMatrix(m)
+    dist, rows, count = dm.topk(q, 20, metric)
+    assert count.tolist() == [20] * len(q)
+    for i in range(len(q)):
+        want_rows, want_d = osearch.topk_rows(metric, 20, q[i], m)
+        assert np.array_equal(rows[i], want_rows), (dim, metric, i)
+        tol = dict(rtol=0, atol=2e-7) if metric == "cosine_sim" else dict(rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(dist[i], want_d, equal_nan=True, **tol)
