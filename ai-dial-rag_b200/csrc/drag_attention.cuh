@@ -259,6 +259,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   const int head = blockIdx.x % heads;
   const int q_tile = blockIdx.x / heads;
   const int seq = blockIdx.y;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch: the QKV GEMM's outputs are visible from here on
   const int tok0 = cu_seqlens[seq];
   const int S = cu_seqlens[seq + 1] - tok0;
   const int row0 = q_tile * rows_per_cta;

@@ -356,6 +356,8 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  tc::pdl_launch_dependents();
+  tc::pdl_wait();   // set-up overlapped the previous kernel's tail
 
   if (warp >= SOFTMAX_WARPS) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(OTHER_REGS));

@@ -116,6 +116,7 @@ pool_normalize_kernel(const bf16* __restrict__ x, const float2* __restrict__ sta
                       float* __restrict__ out) {
   const int seq = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  tc::pdl_wait();   // programmatic dependent launch: the last layer's outputs are visible from here on
   if (seq >= n_seq) return;
   const size_t row = cu_seqlens ? (size_t)cu_seqlens[seq] : (size_t)seq;
   float v[12];
@@ -148,6 +149,8 @@ cls_attention_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ x, c
   const int seq = blockIdx.x;
   const int head = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hidden = heads * HEAD_DIM, ld = 3 * hidden;
+  tc::pdl_launch_dependents();
+  tc::pdl_wait();   // programmatic dependent launch: the QKV GEMM's outputs are visible from here on
   const int tok0 = cu_seqlens[seq];
   const int S = cu_seqlens[seq + 1] - tok0;
   // gather: raw CLS row + statistics
@@ -311,6 +314,9 @@ struct drag_encoder {
   // FFN-up + GELU + FFN-down + residual in one kernel (drag_mlp.cuh) for batches of at least FUSED_MLP_MIN_TOKENS tokens;
   // DRAG_FUSED_MLP=0: always the two GEMM kernels.  Measured (262 144 tokens): 0.52 ms against 0.33 + 0.33 ms.
   bool fused_mlp = true;
+  // programmatic dependent launch of the forward's kernels: each one's set-up (barriers, tensor-memory allocation, descriptor
+  // prefetch) overlaps its predecessor's tail (DRAG_PDL=0: plain stream order)
+  bool pdl = true;
   bool cls_only = true;                           // last layer on the [CLS] rows only (DRAG_CLS_ONLY=0: all rows)
   // optional per-kernel-class timing (bench.py roofline): event pairs recorded around the launches of the bulk workspace
   bool profiling = false;
@@ -318,6 +324,8 @@ struct drag_encoder {
   std::vector<int> prof_class;
   size_t prof_used = 0;
 };
+
+constexpr int PDL_MAX_TOKENS = 16384;
 
 enum KernelClass { KC_EMBED = 0, KC_GEMM_QKV, KC_ATTENTION, KC_GEMM_OUT_LN, KC_GEMM_UP_GELU, KC_GEMM_DOWN_LN, KC_POOL, KC_CLS_TAIL, KC_MLP, KC_COUNT };
 
@@ -395,9 +403,37 @@ int upload_concat_f32(drag_encoder* e, float** dst, std::initializer_list<const 
   return upload_f32(e, dst, tmp.data(), tmp.size());
 }
 
+// One launch path for every kernel of the forward: optional CTA-pair clusters, optional programmatic dependent launch
+// (the kernel must call tc::pdl_wait() before it touches anything an earlier kernel of the stream reads or writes)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = (unsigned)n;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 template <int BLOCK_N, int EPI, int EPI_WARPS, int STAGES, int CG, bool WS = false>
 int launch_gemm(const drag_encoder* e, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tout,
-                const CUtensorMap& tres, const gemm::GemmParams& p, cudaStream_t st) {
+                const CUtensorMap& tres, const gemm::GemmParams& p, cudaStream_t st, bool pdl = false) {
   // tres: the residual rows as 32 x 64 boxes (EPI_RES; the other epilogues ignore it)
   auto kern = gemm::gemm_kernel<BLOCK_N, EPI, EPI_WARPS, STAGES, CG, WS>;
   constexpr size_t smem = gemm::smem_bytes<BLOCK_N, STAGES, EPI_WARPS, CG, WS, EPI>();
@@ -418,30 +454,13 @@ int launch_gemm(const drag_encoder* e, const CUtensorMap& ta, const CUtensorMap&
   const int tiles = m_tiles * (p.N / BLOCK_N);
   const int workers = e->sms / CG;   // CTAs, or CTA pairs (one pair per TPC)
   const int grid = CG * (tiles < workers ? tiles : workers);
-  if (CG == 1) {
-    kern<<<grid, 64 + 32 * EPI_WARPS, smem, st>>>(ta, tw, tout, tres, p);
-    DRAG_CUDA_OK(cudaGetLastError());
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(64 + 32 * EPI_WARPS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    DRAG_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tw, tout, tres, p));
-  }
+  DRAG_CUDA_OK(launch_ex(kern, dim3(grid), dim3(64 + 32 * EPI_WARPS), smem, st, CG, pdl, ta, tw, tout, tres, p));
   return DRAG_OK;
 }
 
 // the fused feed-forward block (drag_mlp.cuh): out = gelu(LN_1(x) W1^T + b_1) W2^T + b_2 + LN_1(x), CTA pairs over 256-token tiles
 int launch_mlp(const drag_encoder* e, const CUtensorMap& tx, const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorMap& tout,
-               const mlp::MlpParams& p, cudaStream_t st) {
+               const mlp::MlpParams& p, cudaStream_t st, bool pdl = false) {
   constexpr size_t smem = mlp::smem_bytes();
   static std::once_flag once[16];
   static cudaError_t attr_err[16];
@@ -454,20 +473,9 @@ int launch_mlp(const drag_encoder* e, const CUtensorMap& tx, const CUtensorMap& 
     return fail(DRAG_ERR_CUDA, "cudaFuncSetAttribute(mlp smem=%zu) failed: %s", smem, cudaGetErrorString(attr_err[dev_slot]));
   const int tiles = (p.M + 2 * mlp::ROWS - 1) / (2 * mlp::ROWS);
   const int pairs = e->sms / 2;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
-  cfg.blockDim = dim3(mlp::THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (p.trace) DRAG_CUDA_OK(cudaLaunchKernelEx(&cfg, mlp::mlp_kernel<true>, tx, tw1, tw2, tout, p));
-  else DRAG_CUDA_OK(cudaLaunchKernelEx(&cfg, mlp::mlp_kernel<false>, tx, tw1, tw2, tout, p));
+  const dim3 grid(2 * (tiles < pairs ? tiles : pairs));
+  if (p.trace) DRAG_CUDA_OK(launch_ex(mlp::mlp_kernel<true>, grid, dim3(mlp::THREADS), smem, st, 2, false, tx, tw1, tw2, tout, p));
+  else DRAG_CUDA_OK(launch_ex(mlp::mlp_kernel<false>, grid, dim3(mlp::THREADS), smem, st, 2, pdl, tx, tw1, tw2, tout, p));
   return DRAG_OK;
 }
 
@@ -480,7 +488,7 @@ constexpr int ATTENTION_TC_ABOVE = 256;
 // attention of the (sequence, head) items of the packed batch whose length is in (len_lo, len_hi]; max_len = the longest
 // of those.  variant 0: mma.sync kernel, 3: tcgen05 kernel (7: with the debug timeline)
 int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* qkv, bf16* ctx, const int32_t* d_cu,
-                     int n_seq, int max_len, int heads, cudaStream_t st, int len_lo = 0, int len_hi = 1 << 30) {
+                     int n_seq, int max_len, int heads, cudaStream_t st, int len_lo = 0, int len_hi = 1 << 30, bool pdl = false) {
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)HEAD_DIM);
   if (variant == 3 || variant == 7) {
     // tcgen05, two softmax groups, P in tensor memory (drag_attention_tc3.cuh); variant 7 = the same with the debug timeline
@@ -497,9 +505,9 @@ int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* q
     const int grid = units < sms ? units : sms;
     const int stages = attn3::unit_stages(max_len);
     if (variant == 7)
-      attn3::attention_tc3_kernel<true><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2, len_lo, len_hi);
+      DRAG_CUDA_OK(launch_ex(attn3::attention_tc3_kernel<true>, dim3(grid), dim3(attn3::THREADS), smem, st, 1, false, tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2, len_lo, len_hi));
     else
-      attn3::attention_tc3_kernel<false><<<grid, attn3::THREADS, smem, st>>>(tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2, len_lo, len_hi);
+      DRAG_CUDA_OK(launch_ex(attn3::attention_tc3_kernel<false>, dim3(grid), dim3(attn3::THREADS), smem, st, 1, pdl, tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2, len_lo, len_hi));
   } else {
     const size_t smem = attn::smem_bytes(max_len);
     // few sequences (the query path): smaller query tiles so that the launch still fills the GPU
@@ -508,7 +516,7 @@ int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* q
     const int q_tiles = (max_len + rows_per_cta - 1) / rows_per_cta;
     for (int s0 = 0; s0 < n_seq; s0 += 65535) {   // gridDim.y limit
       const int n = n_seq - s0 < 65535 ? n_seq - s0 : 65535;
-      attn::attention_kernel<<<dim3(heads * q_tiles, n), attn::WARPS * 32, smem, st>>>(qkv, ctx, d_cu + s0, heads, scale_log2, rows_per_cta, len_lo, len_hi);
+      DRAG_CUDA_OK(launch_ex(attn::attention_kernel, dim3(heads * q_tiles, n), dim3(attn::WARPS * 32), smem, st, 1, pdl, qkv, ctx, d_cu + s0, heads, scale_log2, rows_per_cta, len_lo, len_hi));
     }
   }
   DRAG_CUDA_OK(cudaGetLastError());
@@ -556,6 +564,9 @@ int forward_impl(drag_encoder* e, Workspace& ws, const int32_t* d_ids, const int
   const drag_bert_shape& sh = e->shape;
 
   const bool tap = d_hidden != nullptr;
+  // Programmatic dependent launch pays where kernels are short (the query path: 62 launches of ~10 us, batch-1 forward
+  // 0.69 -> 0.55 ms); on indexing batches, where every kernel fills the GPU for 0.1-0.5 ms, it measured 1 % slower.
+  const bool pdl = e->pdl && total <= PDL_MAX_TOKENS;
   {
     ProfScope prof(e, ws, KC_EMBED, st);
     const int warps_per_block = 8;
@@ -579,7 +590,7 @@ int forward_impl(drag_encoder* e, Workspace& ws, const int32_t* d_ids, const int
     p.N = 3 * HIDDEN; p.K = HIDDEN; p.colc = L.qkv_c; p.cold = L.qkv_d; p.in_stats = ws.stats_x;
     {
       ProfScope prof(e, ws, KC_GEMM_QKV, st);
-      rc = (e->gemm_pairs & 1) ? DRAG_GEMM2_QKV(e, ws.tm_x, L.tp_qkv, ws.ts_qkv, ws.ts_qkv, p, st) : DRAG_GEMM_QKV(e, ws.tm_x, L.tm_qkv, ws.ts_qkv, ws.ts_qkv, p, st);
+      rc = (e->gemm_pairs & 1) ? DRAG_GEMM2_QKV(e, ws.tm_x, L.tp_qkv, ws.ts_qkv, ws.ts_qkv, p, st, pdl) : DRAG_GEMM_QKV(e, ws.tm_x, L.tm_qkv, ws.ts_qkv, ws.ts_qkv, p, st, pdl);
     }
     if (rc) return rc;
     // From here on the last layer works on COMPACT rows (row = sequence) when only the pooled output is wanted:
@@ -590,22 +601,22 @@ int forward_impl(drag_encoder* e, Workspace& ws, const int32_t* d_ids, const int
     if (last_cls) {
       ProfScope prof(e, ws, KC_CLS_TAIL, st);
       const float scale_log2 = 1.4426950408889634f / sqrtf((float)HEAD_DIM);
-      cls_attention_kernel<<<n_seq, sh.heads * 32, 0, st>>>(ws.qkv, ws.x, ws.stats_x, d_cu, sh.heads, scale_log2, ws.ctx, ws.y, ws.stats_y);
-      DRAG_CUDA_OK(cudaGetLastError());
+      DRAG_CUDA_OK(launch_ex(cls_attention_kernel, dim3(n_seq), dim3(sh.heads * 32), 0, st, 1, pdl, (const bf16*)ws.qkv, (const bf16*)ws.x, (const float2*)ws.stats_x,
+                             d_cu, sh.heads, scale_log2, ws.ctx, ws.y, ws.stats_y));
       res = ws.y; mid = ws.x; res_stats = ws.stats_y; mid_stats = ws.stats_x;
       tm_res = &ws.tm_y; ts_res = &ws.ts_y; tm_mid = &ws.tm_x; ts_mid = &ws.ts_x;
       p.M = n_seq;
     } else {
       ProfScope prof(e, ws, KC_ATTENTION, st);
       if (e->attention_variant >= 0) {
-        rc = launch_attention(e->attention_variant, ws.tm_qkv_heads, ws.qkv, ws.ctx, d_cu, n_seq, max_len, sh.heads, st);
+        rc = launch_attention(e->attention_variant, ws.tm_qkv_heads, ws.qkv, ws.ctx, d_cu, n_seq, max_len, sh.heads, st, 0, 1 << 30, pdl);
       } else {
         // every sequence goes to the kernel of its length class whatever else is in the batch, so its embedding does not
         // depend on the batch composition; a mixed batch takes two launches
         rc = DRAG_OK;
-        if (n_long < n_seq) rc = launch_attention(0, ws.tm_qkv_heads, ws.qkv, ws.ctx, d_cu, n_seq, max_short, sh.heads, st, 0, ATTENTION_TC_ABOVE);
+        if (n_long < n_seq) rc = launch_attention(0, ws.tm_qkv_heads, ws.qkv, ws.ctx, d_cu, n_seq, max_short, sh.heads, st, 0, ATTENTION_TC_ABOVE, pdl);
         if (rc == DRAG_OK && n_long > 0)
-          rc = launch_attention(3, ws.tm_qkv_heads, ws.qkv, ws.ctx, d_cu, n_seq, max_len, sh.heads, st, ATTENTION_TC_ABOVE, 1 << 30);
+          rc = launch_attention(3, ws.tm_qkv_heads, ws.qkv, ws.ctx, d_cu, n_seq, max_len, sh.heads, st, ATTENTION_TC_ABOVE, 1 << 30, pdl);
       }
       if (rc) return rc;
     }
@@ -614,7 +625,7 @@ int forward_impl(drag_encoder* e, Workspace& ws, const int32_t* d_ids, const int
     p.residual = res; p.out_stats = mid_stats;
     {
       ProfScope prof(e, ws, last_cls ? KC_CLS_TAIL : KC_GEMM_OUT_LN, st);
-      rc = (e->gemm_pairs & 2) ? DRAG_GEMM2_RES_WS(e, ws.tm_ctx, L.tp_o, *ts_mid, *ts_res, p, st) : DRAG_GEMM_RES(e, ws.tm_ctx, L.tm_o, *ts_mid, *ts_res, p, st);
+      rc = (e->gemm_pairs & 2) ? DRAG_GEMM2_RES_WS(e, ws.tm_ctx, L.tp_o, *ts_mid, *ts_res, p, st, pdl) : DRAG_GEMM_RES(e, ws.tm_ctx, L.tm_o, *ts_mid, *ts_res, p, st, pdl);
     }
     if (rc) return rc;
     if (e->fused_mlp && !last_cls && total >= FUSED_MLP_MIN_TOKENS) {
@@ -623,7 +634,7 @@ int forward_impl(drag_encoder* e, Workspace& ws, const int32_t* d_ids, const int
       mp.M = total; mp.up_c = L.up_c; mp.up_d = L.up_d; mp.down_cold = L.down_cold; mp.down_gamma = L.down_gamma;
       mp.in_stats = mid_stats; mp.out_stats = res_stats; mp.inv_width = 1.0f / HIDDEN; mp.ln_eps = sh.ln_eps;
       ProfScope prof(e, ws, KC_MLP, st);
-      rc = launch_mlp(e, *tm_mid, L.tf_w1, L.tf_w2, res == ws.x ? ws.t32_x : ws.t32_y, mp, st);
+      rc = launch_mlp(e, *tm_mid, L.tf_w1, L.tf_w2, res == ws.x ? ws.t32_x : ws.t32_y, mp, st, pdl);
       if (rc) return rc;
       continue;
     }
@@ -632,8 +643,8 @@ int forward_impl(drag_encoder* e, Workspace& ws, const int32_t* d_ids, const int
     p.residual = nullptr; p.out_stats = nullptr;
     {
       ProfScope prof(e, ws, last_cls ? KC_CLS_TAIL : KC_GEMM_UP_GELU, st);
-      rc = (e->gemm_pairs & 16) ? DRAG_GEMM2_UP_WS(e, *tm_mid, L.tp_up, ws.ts_h, ws.ts_h, p, st)
-           : (e->gemm_pairs & 4) ? DRAG_GEMM2_UP(e, *tm_mid, L.tp_up, ws.ts_h, ws.ts_h, p, st) : DRAG_GEMM_UP(e, *tm_mid, L.tm_up, ws.ts_h, ws.ts_h, p, st);
+      rc = (e->gemm_pairs & 16) ? DRAG_GEMM2_UP_WS(e, *tm_mid, L.tp_up, ws.ts_h, ws.ts_h, p, st, pdl)
+           : (e->gemm_pairs & 4) ? DRAG_GEMM2_UP(e, *tm_mid, L.tp_up, ws.ts_h, ws.ts_h, p, st, pdl) : DRAG_GEMM_UP(e, *tm_mid, L.tm_up, ws.ts_h, ws.ts_h, p, st, pdl);
     }
     if (rc) return rc;
     // res_raw = h . W2^T + b_2 + LN_1(mid_raw)   (+ row statistics of res_raw); LN_2 is applied by the consumers
@@ -641,7 +652,7 @@ int forward_impl(drag_encoder* e, Workspace& ws, const int32_t* d_ids, const int
     p.residual = mid; p.out_stats = res_stats; p.f16_operands = 1;   // h and W2 are fp16
     {
       ProfScope prof(e, ws, last_cls ? KC_CLS_TAIL : KC_GEMM_DOWN_LN, st);
-      rc = (e->gemm_pairs & 8) ? DRAG_GEMM2_RES(e, ws.tm_h, L.tp_down, *ts_res, *ts_mid, p, st) : DRAG_GEMM_RES(e, ws.tm_h, L.tm_down, *ts_res, *ts_mid, p, st);
+      rc = (e->gemm_pairs & 8) ? DRAG_GEMM2_RES(e, ws.tm_h, L.tp_down, *ts_res, *ts_mid, p, st, pdl) : DRAG_GEMM_RES(e, ws.tm_h, L.tm_down, *ts_res, *ts_mid, p, st, pdl);
     }
     if (rc) return rc;
     (void)tm_res;
@@ -657,9 +668,11 @@ int forward_impl(drag_encoder* e, Workspace& ws, const int32_t* d_ids, const int
     ProfScope prof(e, ws, KC_POOL, st);
     const int blocks = (n_seq + 7) / 8;
     if (cls_tail)   // the last layer left compact rows (row = sequence) in y
-      pool_normalize_kernel<<<blocks, 256, 0, st>>>(ws.y, ws.stats_y, fin_g, fin_b, sh.ln_eps, nullptr, n_seq, d_out);
+      DRAG_CUDA_OK(launch_ex(pool_normalize_kernel, dim3(blocks), dim3(256), 0, st, 1, pdl, (const bf16*)ws.y, (const float2*)ws.stats_y, fin_g, fin_b, sh.ln_eps,
+                             (const int*)nullptr, n_seq, d_out));
     else
-      pool_normalize_kernel<<<blocks, 256, 0, st>>>(ws.x, ws.stats_x, fin_g, fin_b, sh.ln_eps, d_cu, n_seq, d_out);
+      DRAG_CUDA_OK(launch_ex(pool_normalize_kernel, dim3(blocks), dim3(256), 0, st, 1, pdl, (const bf16*)ws.x, (const float2*)ws.stats_x, fin_g, fin_b, sh.ln_eps,
+                             (const int*)d_cu, n_seq, d_out));
     DRAG_CUDA_OK(cudaGetLastError());
   }
   return DRAG_OK;
@@ -848,6 +861,8 @@ extern "C" int drag_encoder_create(const drag_bert_shape* shape, const float* co
     if (v && strcmp(v, "mma") == 0) e->attention_variant = 0;
     const char* gm = getenv("DRAG_GEMM_PAIRS");
     if (gm && gm[0] >= '0' && gm[0] <= '9') e->gemm_pairs = atoi(gm) & 31;
+    const char* pd = getenv("DRAG_PDL");
+    if (pd && pd[0] == '0') e->pdl = false;
     const char* fm = getenv("DRAG_FUSED_MLP");
     if (fm && fm[0] == '0') e->fused_mlp = false;
     const char* co = getenv("DRAG_CLS_ONLY");

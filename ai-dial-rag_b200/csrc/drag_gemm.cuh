@@ -238,6 +238,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  tc::pdl_launch_dependents();
+  tc::pdl_wait();   // the set-up above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================

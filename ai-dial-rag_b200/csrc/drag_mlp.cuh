@@ -183,7 +183,7 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ C
     tc::mbar_init(out_free, 2 * EPI_WARPS);
     tc::fence_barrier_init();
   }
-  // the per-column epilogue terms, once (the __syncthreads below publishes them)
+  // the per-column epilogue terms (weights-side constants: not written by any kernel of the forward), once
   for (int i = (int)threadIdx.x; i < INTER / 4; i += THREADS) {
     reinterpret_cast<float4*>(tab1)[i] = __ldg(reinterpret_cast<const float4*>(p.up_c) + i);
     reinterpret_cast<float4*>(tab1 + INTER)[i] = __ldg(reinterpret_cast<const float4*>(p.up_d) + i);
@@ -201,6 +201,8 @@ mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ C
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  tc::pdl_launch_dependents();
+  tc::pdl_wait();   // everything above overlapped the previous kernel's tail
 
   // E1 of one warp: its 16 hidden units of chunk g.  h = gelu(rstd * (acc - mu * colc) + cold) as fp16 pairs, written over the
   // first 8 of the 16 accumulator columns just read: the A operand of G2's k-step `cg`
