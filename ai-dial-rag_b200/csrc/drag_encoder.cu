@@ -20,7 +20,6 @@
 
 #include "drag_attention.cuh"
 #include "drag_attention_tc3.cuh"
-#include "drag_attention_tc4.cuh"
 #include "drag_common.cuh"
 #include "drag_gemm.cuh"
 #include "drag_mlp.cuh"
@@ -311,7 +310,6 @@ struct drag_encoder {
   // 262144 tokens): QKV 0.255 vs 0.267 ms, FFN-up 0.365 vs 0.375, FFN-down 0.339 vs 0.397 in favour of pairs;
   // the out-projection (N = K = 384, epilogue-bound) 0.178 vs 0.202 in favour of single CTAs.  DRAG_GEMM_PAIRS=<mask>.
   int gemm_pairs = 15;
-  int attention_short_variant = 0;                // kernel of the short class (<= 256 tokens) under the default dispatch: 0 = mma.sync, 4 = tcgen05 one job per CTA
   int attention_variant = -1;                     // -1 = by sequence length (launch_attention), 0 = mma.sync kernel, 3 = tcgen05 kernel (DRAG_ATTENTION=mma / tc3)
   // FFN-up + GELU + FFN-down + residual in one kernel (drag_mlp.cuh) for batches of at least FUSED_MLP_MIN_TOKENS tokens;
   // DRAG_FUSED_MLP=0: always the two GEMM kernels.  Measured (262 144 tokens): 0.52 ms against 0.33 + 0.33 ms.
@@ -510,22 +508,6 @@ int launch_attention(int variant, const CUtensorMap& tm_qkv_heads, const bf16* q
       DRAG_CUDA_OK(launch_ex(attn3::attention_tc3_kernel<true>, dim3(grid), dim3(attn3::THREADS), smem, st, 1, false, tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2, len_lo, len_hi));
     else
       DRAG_CUDA_OK(launch_ex(attn3::attention_tc3_kernel<false>, dim3(grid), dim3(attn3::THREADS), smem, st, 1, pdl, tm_qkv_heads, ctx, d_cu, n_seq, heads, max_tiles, stages, split, scale_log2, len_lo, len_hi));
-  } else if (variant == 4) {
-    // tcgen05, one job per CTA, four CTAs per SM (drag_attention_tc4.cuh): sequences of up to 256 tokens
-    DRAG_REQUIRE(max_len <= attn4::MAX_LEN, "attention variant 4 handles sequences of up to %d tokens (got %d)", attn4::MAX_LEN, max_len);
-    const size_t smem = attn4::smem_bytes4(max_len);
-    int sms4 = 148;
-    {
-      int dev = 0;
-      if (cudaGetDevice(&dev) == cudaSuccess && sm_count(dev) > 0) sms4 = sm_count(dev);
-    }
-    unsigned stagger_ns = 2500;
-    if (const char* sn = getenv("DRAG_ATTN4_STAGGER_NS")) stagger_ns = (unsigned)atoi(sn);
-    const int q_tiles = (max_len + attn3::TILE - 1) / attn3::TILE;
-    for (int s0 = 0; s0 < n_seq; s0 += 65535) {   // gridDim.y limit
-      const int n = n_seq - s0 < 65535 ? n_seq - s0 : 65535;
-      DRAG_CUDA_OK(launch_ex(attn4::attention_tc4_kernel, dim3(heads * q_tiles, n), dim3(attn4::THREADS4), smem, st, 1, pdl, tm_qkv_heads, ctx, d_cu + s0, heads, scale_log2, len_lo, len_hi, sms4, stagger_ns));
-    }
   } else {
     const size_t smem = attn::smem_bytes(max_len);
     // few sequences (the query path): smaller query tiles so that the launch still fills the GPU
@@ -548,8 +530,6 @@ int attention_set_attributes() {
   DRAG_CUDA_OK(cudaFuncSetAttribute(attn3::attention_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3_max));
   DRAG_CUDA_OK(cudaFuncSetAttribute(attn3::attention_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3_max));
   DRAG_CUDA_OK(cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::smem_bytes(512)));
-  DRAG_CUDA_OK(cudaFuncSetAttribute(attn4::attention_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn4::smem_bytes4(attn4::MAX_LEN)));
-  DRAG_CUDA_OK(cudaFuncSetAttribute(attn4::attention_tc4_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // four 41 KB CTAs per SM
   return DRAG_OK;
 }
 
@@ -634,7 +614,7 @@ int forward_impl(drag_encoder* e, Workspace& ws, const int32_t* d_ids, const int
         // every sequence goes to the kernel of its length class whatever else is in the batch, so its embedding does not
         // depend on the batch composition; a mixed batch takes two launches
         rc = DRAG_OK;
-        if (n_long < n_seq) rc = launch_attention(e->attention_short_variant, ws.tm_qkv_heads, ws.qkv, ws.ctx, d_cu, n_seq, max_short, sh.heads, st, 0, ATTENTION_TC_ABOVE, pdl);
+        if (n_long < n_seq) rc = launch_attention(0, ws.tm_qkv_heads, ws.qkv, ws.ctx, d_cu, n_seq, max_short, sh.heads, st, 0, ATTENTION_TC_ABOVE, pdl);
         if (rc == DRAG_OK && n_long > 0)
           rc = launch_attention(3, ws.tm_qkv_heads, ws.qkv, ws.ctx, d_cu, n_seq, max_len, sh.heads, st, ATTENTION_TC_ABOVE, 1 << 30, pdl);
       }
@@ -878,8 +858,6 @@ extern "C" int drag_encoder_create(const drag_bert_shape* shape, const float* co
   {
     const char* v = getenv("DRAG_ATTENTION");
     if (v && strcmp(v, "tc3") == 0) e->attention_variant = 3;
-    if (v && strcmp(v, "tc4") == 0) e->attention_short_variant = 4;
-    if (v && strcmp(v, "auto_mma") == 0) e->attention_short_variant = 0;
     if (v && strcmp(v, "mma") == 0) e->attention_variant = 0;
     const char* gm = getenv("DRAG_GEMM_PAIRS");
     if (gm && gm[0] >= '0' && gm[0] <= '9') e->gemm_pairs = atoi(gm) & 31;
@@ -1078,7 +1056,7 @@ extern "C" int drag_debug_attention(int device, int variant, const void* d_qkv, 
                                     int n_seq, int n_tokens, int max_len, int heads, void* stream) {
   DRAG_REQUIRE(d_qkv && d_ctx && d_cu_seqlens && n_seq >= 1 && heads >= 1 && n_tokens >= 1, "drag_debug_attention: bad arguments");
   DRAG_REQUIRE(max_len >= 1 && max_len <= 512, "drag_debug_attention: max_len must be in 1..512");
-  DRAG_REQUIRE(variant == 0 || variant == 3 || variant == 4 || variant == 7, "drag_debug_attention: variant 0 (mma.sync), 3 (tcgen05, persistent, two softmax groups), 4 (tcgen05, one job per CTA, <= 256 tokens), 7 (3 with the debug timeline)");
+  DRAG_REQUIRE(variant == 0 || variant == 3 || variant == 7, "drag_debug_attention: variant 0 (mma.sync), 3 (tcgen05, two softmax groups, P in tensor memory), 7 (3 with the debug timeline)");
   DeviceGuard guard(device);
   if (!guard.ok) return fail(DRAG_ERR_DEVICE, "drag_debug_attention: cannot select device %d", device);
   int rc = attention_set_attributes();

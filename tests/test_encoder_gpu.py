@@ -147,9 +147,9 @@ def test_fused_mlp_vs_torch(M):
     assert (got - out2.float()).abs().max().item() <= 0.01 * scale + 0.03
 
 
-@pytest.mark.parametrize("variant,lens", [(v, l) for v in (3, 0) for l in ([1, 2, 17, 64, 65, 128, 256, 300, 512, 33], [512], [300, 77], [130] * 4)]
-                         + [(4, l) for l in ([1, 2, 17, 63, 64, 65, 127, 128, 129, 200, 256, 33], [256], [193, 77], [130] * 4)],
-                         ids=lambda x: str(x) if isinstance(x, int) else "-".join(map(str, x[:4])) + ("+" if len(x) > 4 else ""))
+@pytest.mark.parametrize("lens", [[1, 2, 17, 64, 65, 128, 256, 300, 512, 33], [512], [300, 77], [130] * 4],
+                         ids=["ragged10", "one512", "two", "four130"])
+@pytest.mark.parametrize("variant", [3, 0])
 def test_attention_vs_torch(variant, lens):
     """Every attention kernel against torch fp32 softmax(QK^T/sqrt(32))V per packed sequence; the short
     batches exercise the 128- and 64-query tiles the mma.sync kernel picks when few sequences are in flight."""
@@ -176,14 +176,14 @@ def test_attention_vs_torch(variant, lens):
         assert err <= 0.03, (variant, n, err)
 
 
-@pytest.mark.parametrize("variant", [3, 0, 4])
+@pytest.mark.parametrize("variant", [3, 0])
 def test_attention_peaked_garbage_tail_and_batch_invariance(variant):
     """What the encoder does to an attention kernel and random inputs do not: peaked logits (the reference of a row is
     raised between key blocks), NaN in the never-written rows behind the last sequence (0 x NaN must not reach anybody's
     output), and bit-identical rows whether a sequence is processed alone or inside a batch."""
     native, lib = _lib()
     heads, hd = 12, 32
-    lens = [5, 130, 101, 2, 257, 64, 400] if variant != 4 else [5, 130, 101, 2, 256, 64, 200]   # variant 4: <= 256 tokens
+    lens = [5, 130, 101, 2, 257, 64, 400]
     cu = np.zeros(len(lens) + 1, dtype=np.int32)
     cu[1:] = np.cumsum(lens)
     T = int(cu[-1])
