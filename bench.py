@@ -805,6 +805,22 @@ def main() -> None:
     e2e_s = time.perf_counter() - t0
     barrier()
 
+    # ---------------- ragged variant: lengths uniform 16..256, packed -- no padding work ----------------
+    ragged = None
+    if rank == 0:
+        from tests.synth import synth_token_batch
+        r_ids, r_cu = synth_token_batch(seed=77, n_seq=chunks, seq_len=SEQ_LEN, ragged=True)
+        for _ in range(2):
+            enc.embed_packed(r_ids, r_cu)
+        t0 = time.perf_counter()
+        for _ in range(max(3, args.steps // 2)):
+            enc.embed_packed(r_ids, r_cu)
+        r_s = (time.perf_counter() - t0) / max(3, args.steps // 2)
+        ragged = {"workload": f"{chunks} chunks, lengths uniform in [16, {SEQ_LEN}], packed (host ids in, host embeddings out)",
+                  "tokens": int(r_cu[-1]), "chunks_per_s": chunks / r_s, "tokens_per_s": float(r_cu[-1]) / r_s,
+                  "padded_tokens_a_pad_to_longest_batch_would_process": chunks * SEQ_LEN}
+    barrier()
+
     if world > 1:
         t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -900,6 +916,10 @@ def main() -> None:
         "parity": {},
         "extra": {"kernels": breakdown},
     }
+    if ragged is not None:
+        line["extra"]["ragged_16_256"] = ragged
+        line["e2e"]["ragged_16_256_chunks_per_s"] = ragged["chunks_per_s"]
+        line["e2e"]["ragged_16_256_tokens_per_s"] = ragged["tokens_per_s"]
     parity = line["parity"]
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
