@@ -89,6 +89,7 @@ _SIGNATURES = {
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+ABI_VERSION = 2   # include/drag_b200.h DRAG_ABI_VERSION (2: nine profile classes, drag_debug_mlp, attention trace entry points)
 
 _lib = None
 _lock = threading.Lock()
@@ -113,6 +114,9 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
+        if lib.drag_abi_version() != ABI_VERSION:   # a stale build: array sizes / signatures below would not match
+            raise DragError(-1, f"{LIB_PATH} has ABI version {lib.drag_abi_version()}, this package needs {ABI_VERSION}: "
+                                "rebuild it with `python ai-dial-rag_b200/csrc/build.py`")
         _lib = lib
     return _lib
 

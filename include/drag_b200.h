@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define DRAG_ABI_VERSION 1
+#define DRAG_ABI_VERSION 2   /* 2: drag_encoder_profile_end fills nine classes; drag_debug_mlp; attention trace entry points */
 
 enum drag_status {
   DRAG_OK = 0,

@@ -44,7 +44,7 @@ def test_python_binding_covers_header(lib_path):
 
     assert set(declared_functions()) == set(_native.EXPORTED_SYMBOLS)
     lib = _native.load()
-    assert lib.drag_abi_version() == 1
+    assert lib.drag_abi_version() == 2
 
 
 def test_errors_surface_as_exceptions(lib_path):
